@@ -1,0 +1,445 @@
+/*
+ * lrf_oracle.c -- CPU restatement (plain C, fp32, OpenMP over rays) of the reference's
+ * volume-rendering hot path.  TEST INFRASTRUCTURE ONLY -- see lrf_oracle.h.
+ *
+ * Every function cites the reference lines (relative to /root/reference/localTensoRF) whose
+ * behaviour it restates.  Compiled with -ffp-contract=off so that a*b+c is two roundings like
+ * the separate ATen kernels of the reference.
+ */
+#include "lrf_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static const int MAT0[3] = {0, 0, 1}; /* matMode[i][0]  models/tensorBase.py:274 */
+static const int MAT1[3] = {1, 2, 2}; /* matMode[i][1] */
+static const int VEC[3] = {2, 1, 0};  /* vecMode        models/tensorBase.py:275 */
+
+/* ---- utils/ray_utils.py:9-12  contract() ------------------------------------------------- */
+static inline void contract3(float *p) {
+  float n = fmaxf(fmaxf(fabsf(p[0]), fabsf(p[1])), fabsf(p[2]));
+  if (n < 1e-6f) n = 1e-6f;                 /* torch.clamp(x.abs().amax(-1), 1e-6) */
+  if (!(n <= 1.0f)) {                       /* torch.where(x_norm <= 1, x, ...) */
+    float s = (2.0f * n - 1.0f) / (n * n);
+    p[0] = s * p[0]; p[1] = s * p[1]; p[2] = s * p[2];
+  }
+}
+
+void orc_contract(float *xyz, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) contract3(xyz + 3 * i);
+}
+
+/* ---- models/tensorBase.py:419-437  sample_ray_contracted(): the per-batch distance table --- */
+int32_t orc_sample_table(int32_t nSamples, const float *j1, const float *j2, float *z) {
+  int32_t N = nSamples / 6;                               /* :421 */
+  for (int32_t k = 0; k < N; ++k) {
+    float t = (float)k / (float)N;                        /* linspace(0,N-1,N)/N  :423-425 */
+    float a = t, b = t;
+    if (j1) a = t + j1[k] / (float)N;                     /* :430 */
+    if (j2) b = t + j2[k] / (float)N;                     /* :431 */
+    float near_inv = 1.0f, far_inv = 0.001f;              /* near, far = [1, 1e3]  :433 */
+    float inv = 1.0f / (near_inv * (1.0f - b) + far_inv * b); /* :435 */
+    z[k] = a + 0.1f;                                      /* :437 */
+    z[N + k] = inv + 0.1f;
+  }
+  return 2 * N;
+}
+
+/* ---- ATen grid_sampler semantics (align_corners=True)  -- call sites tensoRF.py:135-146 ----- */
+static inline float unnormalize_border(float c, int size) {
+  float x = ((c + 1.0f) / 2.0f) * (float)(size - 1);     /* grid_sampler_unnormalize */
+  x = fminf((float)(size - 1), fmaxf(x, 0.0f));           /* padding_mode="border": clip */
+  return x;
+}
+
+/* bilinear sample of C channels of plane [C][H][W] at normalised (x -> W, y -> H) */
+static inline void bilinear_plane(const float *plane, int C, int H, int W, float x, float y,
+                                  float *out) {
+  float ix = unnormalize_border(x, W), iy = unnormalize_border(y, H);
+  float fx0 = floorf(ix), fy0 = floorf(iy);
+  int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+  float tx = ix - fx0, ty = iy - fy0;
+  float wnw = (1.0f - tx) * (1.0f - ty), wne = tx * (1.0f - ty);
+  float wsw = (1.0f - tx) * ty, wse = tx * ty;
+  int okx1 = x1 <= W - 1, oky1 = y1 <= H - 1; /* out-of-range corners are skipped (weight 0) */
+  for (int c = 0; c < C; ++c) {
+    const float *p = plane + (size_t)c * H * W;
+    float v = p[(size_t)y0 * W + x0] * wnw;
+    if (okx1) v += p[(size_t)y0 * W + x1] * wne;
+    if (oky1) v += p[(size_t)y1 * W + x0] * wsw;
+    if (okx1 && oky1) v += p[(size_t)y1 * W + x1] * wse;
+    out[c] = v;
+  }
+}
+
+/* line [C][L] sampled as a [C][L][1] image at (0, y): a 1-D lerp  (tensoRF.py:141-146) */
+static inline void linear_line(const float *line, int C, int L, float y, float *out) {
+  float iy = unnormalize_border(y, L);
+  float fy0 = floorf(iy);
+  int y0 = (int)fy0, y1 = y0 + 1;
+  float ty = iy - fy0;
+  int oky1 = y1 <= L - 1;
+  for (int c = 0; c < C; ++c) {
+    const float *p = line + (size_t)c * L;
+    float v = p[y0] * (1.0f - ty);
+    if (oky1) v += p[y1] * ty;
+    out[c] = v;
+  }
+}
+
+#define ORC_MAX_COMP 64
+
+/* Transposed copies of the dense weights so the inner loops run over outputs (vectorisable by the
+ * compiler WITHOUT reassociating the sum over inputs: every output still accumulates k = 0,1,2..
+ * in order, exactly like the plain dot product). */
+typedef struct OrcPrep {
+  float *basisT; /* [sum n_acomp][app_dim] */
+  float *w1T;    /* [in1][featureC] */
+  float *w2T;    /* [featureC][featureC] */
+} OrcPrep;
+
+static float *transpose_(const float *w, int rows, int cols) {
+  float *t = (float *)malloc(sizeof(float) * (size_t)rows * cols);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) t[(size_t)c * rows + r] = w[(size_t)r * cols + c];
+  return t;
+}
+
+static void prep_make(const OrcField *f, OrcPrep *p) {
+  int n = f->n_acomp[0] + f->n_acomp[1] + f->n_acomp[2];
+  p->basisT = transpose_(f->basis, f->app_dim, n);
+  p->w1T = transpose_(f->w1, f->featureC, f->app_dim * (1 + 2 * f->fea_pe));
+  p->w2T = transpose_(f->w2, f->featureC, f->featureC);
+}
+
+static void prep_free(OrcPrep *p) { free(p->basisT); free(p->w1T); free(p->w2T); }
+
+/* ---- models/tensoRF.py:112-151  compute_densityfeature() ------------------------------------ */
+static inline float density_feature1(const OrcField *f, const float *q) {
+  float pc[ORC_MAX_COMP], lc[ORC_MAX_COMP];
+  float sigma = 0.0f;
+  for (int i = 0; i < 3; ++i) {
+    int W = f->grid[MAT0[i]], H = f->grid[MAT1[i]], L = f->grid[VEC[i]], C = f->n_dcomp[i];
+    bilinear_plane(f->dplane[i], C, H, W, q[MAT0[i]], q[MAT1[i]], pc);
+    linear_line(f->dline[i], C, L, q[VEC[i]], lc);
+    float s = 0.0f;
+    for (int c = 0; c < C; ++c) s += pc[c] * lc[c];       /* torch.sum(plane*line, dim=0) */
+    sigma = sigma + s;                                    /* :147 */
+  }
+  return sigma;
+}
+
+void orc_density_feature(const OrcField *f, const float *xyz_norm, int64_t M, float *out) {
+  for (int64_t m = 0; m < M; ++m) out[m] = density_feature1(f, xyz_norm + 3 * m);
+}
+
+/* ---- models/tensoRF.py:153-196  compute_appfeature() ---------------------------------------- */
+static inline void app_feature1(const OrcField *f, const OrcPrep *pr, const float *q,
+                                float *out /*[app_dim]*/) {
+  float prod[3 * ORC_MAX_COMP], pc[ORC_MAX_COMP], lc[ORC_MAX_COMP];
+  int n = 0;
+  for (int i = 0; i < 3; ++i) {
+    int W = f->grid[MAT0[i]], H = f->grid[MAT1[i]], L = f->grid[VEC[i]], C = f->n_acomp[i];
+    bilinear_plane(f->aplane[i], C, H, W, q[MAT0[i]], q[MAT1[i]], pc);
+    linear_line(f->aline[i], C, L, q[VEC[i]], lc);
+    for (int c = 0; c < C; ++c) prod[n++] = pc[c] * lc[c]; /* cat over planes, :192-196 */
+  }
+  int A = f->app_dim;                                     /* basis_mat, bias=False :196 */
+  for (int o = 0; o < A; ++o) out[o] = 0.0f;
+  for (int k = 0; k < n; ++k) {
+    const float *w = pr->basisT + (size_t)k * A;
+    float x = prod[k];
+    for (int o = 0; o < A; ++o) out[o] += w[o] * x;
+  }
+}
+
+void orc_app_feature(const OrcField *f, const float *xyz_norm, int64_t M, float *out) {
+  OrcPrep pr; prep_make(f, &pr);
+  for (int64_t m = 0; m < M; ++m)
+    app_feature1(f, &pr, xyz_norm + 3 * m, out + (size_t)m * f->app_dim);
+  prep_free(&pr);
+}
+
+/* ---- models/tensorBase.py:14-21  positional_encoding() -------------------------------------- */
+/* out[2*D*F]: sin block then cos block, index d*F+f = pos[d] * 2^f */
+static inline void pos_enc(const float *pos, int D, int F, float *out) {
+  for (int d = 0; d < D; ++d)
+    for (int fq = 0; fq < F; ++fq) {
+      float v = pos[d] * (float)(1 << fq);
+      out[d * F + fq] = sinf(v);
+      out[D * F + d * F + fq] = cosf(v);
+    }
+}
+
+static inline float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+/* ---- models/tensorBase.py:97-135  MLPRender_Fea_late_view.forward() -------------------------- */
+#define ORC_MAX_IN 1024
+static inline void mlp1(const OrcField *f, const OrcPrep *pr, const float *feat,
+                        const float *vd, int refine, float *rgb) {
+  int A = f->app_dim, Fc = f->featureC;
+  int in1 = A * (1 + 2 * f->fea_pe);
+  int inv = 3 * (1 + 2 * f->view_pe);
+  float x[ORC_MAX_IN], h1[ORC_MAX_IN], h2[ORC_MAX_IN + 64];
+  memcpy(x, feat, sizeof(float) * A);
+  if (f->fea_pe > 0) {
+    if (refine) pos_enc(feat, A, f->fea_pe, x + A);       /* :118-119 */
+    else memset(x + A, 0, sizeof(float) * (in1 - A));     /* :121-125 */
+  }
+  for (int o = 0; o < Fc; ++o) h1[o] = 0.0f;              /* Linear + ReLU :105,110 */
+  for (int k = 0; k < in1; ++k) {
+    const float *w = pr->w1T + (size_t)k * Fc;
+    float xv = x[k];
+    for (int o = 0; o < Fc; ++o) h1[o] += w[o] * xv;
+  }
+  for (int o = 0; o < Fc; ++o) { float s = h1[o] + f->b1[o]; h1[o] = s > 0.0f ? s : 0.0f; }
+  for (int o = 0; o < Fc; ++o) h2[o] = 0.0f;              /* Linear + ReLU :106,110 */
+  for (int k = 0; k < Fc; ++k) {
+    const float *w = pr->w2T + (size_t)k * Fc;
+    float xv = h1[k];
+    for (int o = 0; o < Fc; ++o) h2[o] += w[o] * xv;
+  }
+  for (int o = 0; o < Fc; ++o) { float s = h2[o] + f->b2[o]; h2[o] = s > 0.0f ? s : 0.0f; }
+  h2[Fc] = vd[0]; h2[Fc + 1] = vd[1]; h2[Fc + 2] = vd[2];  /* cat([inter, viewdirs, PE]) :126-131 */
+  if (f->view_pe > 0) pos_enc(vd, 3, f->view_pe, h2 + Fc + 3);
+  for (int o = 0; o < 3; ++o) {                           /* mlp_view + sigmoid :132-133 */
+    const float *w = f->w3 + (size_t)o * (Fc + inv);
+    float s = 0.0f;
+    for (int k = 0; k < Fc + inv; ++k) s += w[k] * h2[k];
+    s += f->b3[o];
+    rgb[o] = sigmoidf_(s);
+  }
+}
+
+void orc_mlp_late_view(const OrcField *f, const float *feat, const float *viewdirs, int64_t M,
+                       int refine, float *rgb) {
+  OrcPrep pr; prep_make(f, &pr);
+  for (int64_t m = 0; m < M; ++m)
+    mlp1(f, &pr, feat + (size_t)m * f->app_dim, viewdirs + 3 * m, refine, rgb + 3 * m);
+  prep_free(&pr);
+}
+
+/* ---- models/tensorBase.py:51-58  AlphaGridMask.sample_alpha(): 3-D grid_sample, trilinear,
+ *      zero padding, align_corners=True; volume [D][H][W], x->W, y->H, z->D ------------------ */
+static inline float alpha_mask1(const OrcField *f, const float *p) {
+  int D = f->alpha_dims[0], H = f->alpha_dims[1], W = f->alpha_dims[2];
+  float q[3];
+  for (int a = 0; a < 3; ++a) {                           /* AlphaGridMask.normalize_coord :57-58 */
+    float inv = 1.0f / (f->alpha_aabb[3 + a] - f->alpha_aabb[a]) * 2.0f; /* invgridSize :45 */
+    q[a] = (p[a] - f->alpha_aabb[a]) * inv - 1.0f;
+  }
+  float ix = ((q[0] + 1.0f) / 2.0f) * (float)(W - 1);
+  float iy = ((q[1] + 1.0f) / 2.0f) * (float)(H - 1);
+  float iz = ((q[2] + 1.0f) / 2.0f) * (float)(D - 1);
+  float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+  int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+  float tx = ix - fx, ty = iy - fy, tz = iz - fz;
+  float v = 0.0f;
+  for (int dz = 0; dz < 2; ++dz)
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) {
+        int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
+        if (xx < 0 || xx >= W || yy < 0 || yy >= H || zz < 0 || zz >= D) continue; /* zeros pad */
+        float w = (dx ? tx : 1.0f - tx) * (dy ? ty : 1.0f - ty) * (dz ? tz : 1.0f - tz);
+        v += f->alpha_vol[((size_t)zz * H + yy) * W + xx] * w;
+      }
+  return v;
+}
+
+void orc_alpha_mask_sample(const OrcField *f, const float *xyz, int64_t M, float *out) {
+  for (int64_t m = 0; m < M; ++m) out[m] = alpha_mask1(f, xyz + 3 * m);
+}
+
+/* ---- models/tensorBase.py:495-499  feature2density() ---------------------------------------- */
+static inline float feature2density(const OrcField *f, float x) {
+  if (f->act == 0) {
+    x = x + f->density_shift;
+    return x > 20.0f ? x : log1pf(expf(x));               /* F.softplus, beta=1, threshold=20 */
+  }
+  return x > 0.0f ? x : 0.0f;                             /* F.relu(density_features) */
+}
+
+/* ---- models/tensorBase.py:23-32  alpha2weights() -------------------------------------------- */
+static inline void alpha2weights(float *alpha, int S, float *w) {
+  alpha[S - 1] = 1.0f;                                    /* :24 */
+  float T = 1.0f;
+  for (int k = 0; k < S; ++k) {
+    w[k] = alpha[k] * T;                                  /* :31 */
+    T = T * ((1.0f - alpha[k]) + 1e-10f);                 /* cumprod([1, 1-alpha+1e-10]) :25-30 */
+  }
+}
+
+/* ---- models/tensorBase.py:567-636  TensorBase.forward() for one ray ------------------------- */
+static void render_ray(const OrcField *f, const OrcPrep *pr, const float *ray, const float *z, int S, int white_bg,
+                       float floater_thresh, int refine, float *rgb, float *depth, float *weights,
+                       float *acc_out, int32_t *n_app, float *alpha, float *w, float *xyz) {
+  const float *o = ray, *d = ray + 3;
+  float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);  /* :579 */
+  float vd[3] = {d[0] / nrm, d[1] / nrm, d[2] / nrm};          /* :580 */
+  float inv_aabb[3];
+  for (int a = 0; a < 3; ++a) inv_aabb[a] = 2.0f / (f->aabb[3 + a] - f->aabb[a]); /* :321 */
+
+  for (int k = 0; k < S; ++k) {
+    float p[3] = {o[0] + vd[0] * z[k], o[1] + vd[1] * z[k], o[2] + vd[2] * z[k]}; /* :438 */
+    contract3(p);                                                                /* :440 */
+    int valid = 1;                                         /* mask_outbbox all False :442 */
+    if (f->alpha_vol) valid = alpha_mask1(f, p) > 0.0f;    /* :593-598 */
+    if (k == S - 1) valid = 0;                             /* ray_valid[:, -1] = 0 :600 */
+    float q[3];
+    for (int a = 0; a < 3; ++a) q[a] = (p[a] - f->aabb[a]) * inv_aabb[a] - 1.0f; /* :342-345,602 */
+    xyz[3 * k] = q[0]; xyz[3 * k + 1] = q[1]; xyz[3 * k + 2] = q[2];
+    float sigma = 0.0f;
+    if (valid) sigma = feature2density(f, density_feature1(f, q));              /* :603-608 */
+    float dist = (k < S - 1) ? (z[k + 1] - z[k]) : 0.0f;                         /* :584-587 */
+    alpha[k] = 1.0f - expf(-sigma * dist * f->distance_scale);                   /* :610 */
+  }
+  alpha2weights(alpha, S, w);                                                    /* :612 */
+  float acc = 0.0f, dsum = 0.0f;
+  for (int k = 0; k < S; ++k) { acc += w[k]; dsum += w[k] * z[k]; }             /* :614-615 */
+  *depth = dsum / nrm;
+  if (floater_thresh > 0.0f) {                                                   /* :617-620 */
+    float idx = 0.0f;
+    for (int k = 0; k < S; ++k) idx += w[k] * (float)k;
+    for (int k = 0; k < S; ++k)
+      if ((float)k < idx * floater_thresh) alpha[k] = 0.0f;
+    alpha2weights(alpha, S, w);
+  }
+  float c[3] = {0.0f, 0.0f, 0.0f};
+  int napp = 0;
+  float feat[ORC_MAX_IN], col[3];
+  for (int k = 0; k < S; ++k) {
+    if (!(w[k] > f->weight_thres)) continue;                                     /* :622 */
+    app_feature1(f, pr, xyz + 3 * k, feat);                                        /* :624-626 */
+    mlp1(f, pr, feat, vd, refine, col);                                            /* :627-630 */
+    c[0] += w[k] * col[0]; c[1] += w[k] * col[1]; c[2] += w[k] * col[2];         /* :632 */
+    ++napp;
+  }
+  if (white_bg) { float bg = 1.0f - acc; c[0] += bg; c[1] += bg; c[2] += bg; }   /* :633-634 */
+  rgb[0] = c[0]; rgb[1] = c[1]; rgb[2] = c[2];
+  if (weights) memcpy(weights, w, sizeof(float) * S);
+  if (acc_out) *acc_out = acc;
+  if (n_app) *n_app = napp;
+}
+
+void orc_field_forward(const OrcField *f, const float *rays, int64_t N, const float *z, int32_t S,
+                       int white_bg, float floater_thresh, int refine, float *rgb, float *depth,
+                       float *weights, float *acc, int32_t *n_app, int n_threads) {
+#ifdef _OPENMP
+  if (n_threads <= 0) n_threads = omp_get_max_threads();
+#else
+  n_threads = 1;
+#endif
+  OrcPrep pr; prep_make(f, &pr);
+#pragma omp parallel num_threads(n_threads)
+  {
+    float *alpha = (float *)malloc(sizeof(float) * S);
+    float *w = (float *)malloc(sizeof(float) * S);
+    float *xyz = (float *)malloc(sizeof(float) * 3 * S);
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t r = 0; r < N; ++r)
+      render_ray(f, &pr, rays + 6 * r, z, S, white_bg, floater_thresh, refine, rgb + 3 * r, depth + r,
+                 weights ? weights + (size_t)r * S : NULL, acc ? acc + r : NULL,
+                 n_app ? n_app + r : NULL, alpha, w, xyz);
+    free(alpha); free(w); free(xyz);
+  }
+  prep_free(&pr);
+}
+
+/* ---- utils/utils.py:381-388  sixD_to_mtx() --------------------------------------------------- */
+void orc_sixD_to_mtx(const float *r6, int64_t V, float *R) {
+  for (int64_t v = 0; v < V; ++v) {
+    const float *r = r6 + 6 * v; /* [3][2]: r[a*2+c] */
+    float b1[3] = {r[0], r[2], r[4]}, a2[3] = {r[1], r[3], r[5]}, b2[3], b3[3];
+    float n1 = sqrtf(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
+    for (int a = 0; a < 3; ++a) b1[a] = b1[a] / n1;
+    float dot = b1[0] * a2[0] + b1[1] * a2[1] + b1[2] * a2[2];
+    for (int a = 0; a < 3; ++a) b2[a] = a2[a] - dot * b1[a];
+    float n2 = sqrtf(b2[0] * b2[0] + b2[1] * b2[1] + b2[2] * b2[2]);
+    for (int a = 0; a < 3; ++a) b2[a] = b2[a] / n2;
+    b3[0] = b1[1] * b2[2] - b1[2] * b2[1];
+    b3[1] = b1[2] * b2[0] - b1[0] * b2[2];
+    b3[2] = b1[0] * b2[1] - b1[1] * b2[0];
+    float *M = R + 9 * v; /* stack([b1,b2,b3], dim=-1): columns */
+    for (int a = 0; a < 3; ++a) { M[a * 3 + 0] = b1[a]; M[a * 3 + 1] = b2[a]; M[a * 3 + 2] = b3[a]; }
+  }
+}
+
+/* ---- local_tensorfs.py:23-29 ids2pixel; ray_utils.py:14-37 directions ------------------------ */
+void orc_ray_directions(const int64_t *ray_ids, int64_t N, int32_t W, int32_t H, int fov360,
+                        float focal, float cx, float cy, float *dirs, int64_t *ij) {
+  const float pi = 3.14159265358979323846f;
+  for (int64_t r = 0; r < N; ++r) {
+    int64_t col = ray_ids[r] % W, row = (ray_ids[r] / W) % H;
+    if (ij) { ij[2 * r] = col; ij[2 * r + 1] = row; }
+    float i = (float)col + 0.5f, j = (float)row + 0.5f;
+    if (fov360) {                                        /* get_ray_directions_360 :32-37 */
+      float phi = j * pi / (float)H - pi / 2.0f;
+      float theta = i * 2.0f * pi / (float)W + pi;
+      dirs[3 * r] = cosf(phi) * sinf(theta);             /* sphere2xyz :26-30, r = 1 */
+      dirs[3 * r + 1] = sinf(phi);
+      dirs[3 * r + 2] = cosf(phi) * cosf(theta);
+    } else {                                             /* get_ray_directions_lean :14-24 */
+      dirs[3 * r] = (i - cx) / focal;
+      dirs[3 * r + 1] = -(j - cy) / focal;
+      dirs[3 * r + 2] = -1.0f;
+    }
+  }
+}
+
+/* ---- local_tensorfs.py:382-499  LocalTensorfs.forward() -------------------------------------- */
+void orc_local_forward(const OrcField *fields, int32_t n_fields, const float *const *zs,
+                       const int32_t *Ss, const int64_t *ray_ids, int64_t N, int32_t W, int32_t H,
+                       int fov360, float focal, float cx, float cy, const float *cam2world,
+                       int64_t V, const float *world2rf, const float *blend, const float *exposure,
+                       int white_bg, float floater_thresh, int refine, float *rgb, float *depth,
+                       float *dirs, int n_threads) {
+  orc_ray_directions(ray_ids, N, W, H, fov360, focal, cx, cy, dirs, NULL);      /* :397-401 */
+  int64_t per_view = N / V;                                                      /* :437 */
+  float *rays = (float *)malloc(sizeof(float) * 6 * N);
+  float *rgb_t = (float *)malloc(sizeof(float) * 3 * N);
+  float *depth_t = (float *)malloc(sizeof(float) * N);
+  memset(rgb, 0, sizeof(float) * 3 * N);                                         /* :439-440 */
+  memset(depth, 0, sizeof(float) * N);
+  for (int32_t k = 0; k < n_fields; ++k) {
+    float colsum = 0.0f;                                                         /* :418 */
+    for (int64_t v = 0; v < V; ++v) colsum += blend[v * n_fields + k];
+    if (colsum == 0.0f) continue;
+    for (int64_t r = 0; r < N; ++r) {                                            /* :427-428,455-456 */
+      const float *c2w = cam2world + 12 * (r / per_view);
+      const float *dc = dirs + 3 * r;
+      float *ray = rays + 6 * r;
+      for (int a = 0; a < 3; ++a) {
+        ray[a] = c2w[a * 4 + 3] + world2rf[3 * k + a];
+        float s = 0.0f;                                                          /* bmm, ray_utils.py:52 */
+        for (int b = 0; b < 3; ++b) s += c2w[a * 4 + b] * dc[b];
+        ray[3 + a] = s;
+      }
+    }
+    orc_field_forward(&fields[k], rays, N, zs[k], Ss[k], white_bg, floater_thresh, refine, rgb_t,
+                      depth_t, NULL, NULL, NULL, n_threads);                     /* :458-465 */
+    for (int64_t r = 0; r < N; ++r) {                                            /* :467-474 */
+      float bw = blend[(r / per_view) * n_fields + k];
+      for (int a = 0; a < 3; ++a) rgb[3 * r + a] = rgb[3 * r + a] + rgb_t[3 * r + a] * bw;
+      depth[r] = depth[r] + depth_t[r] * bw;
+    }
+  }
+  for (int64_t r = 0; r < N; ++r) {
+    float *c = rgb + 3 * r;
+    if (exposure) {                                                              /* :481-496 */
+      const float *E = exposure + 9 * (r / per_view);
+      float o[3];
+      for (int a = 0; a < 3; ++a) {
+        float s = 0.0f;
+        for (int b = 0; b < 3; ++b) s += E[a * 3 + b] * c[b];
+        o[a] = s;
+      }
+      c[0] = o[0]; c[1] = o[1]; c[2] = o[2];
+    }
+    for (int a = 0; a < 3; ++a) c[a] = fminf(1.0f, fmaxf(0.0f, c[a]));          /* :497 */
+  }
+  free(rays); free(rgb_t); free(depth_t);
+}
