@@ -1,0 +1,145 @@
+/*
+ * localrf_b200.h -- C ABI of the B200-native render path of localrf.
+ *
+ * This is the drop-in boundary for the per-ray-batch volume-rendering hot path of
+ * facebookresearch/localrf (reference at localTensoRF/, commit 3905e39):
+ *
+ *     LocalTensorfs.forward      local_tensorfs.py:382-499   (ray generation, per-field render,
+ *                                                             blend, exposure, clamp)
+ *     TensorBase.forward         models/tensorBase.py:567-636 (sample, contract, density,
+ *                                                             alpha/T/weights, floater filter,
+ *                                                             appearance, MLP, composite)
+ *     compute_densityfeature     models/tensoRF.py:112-151
+ *     compute_appfeature         models/tensoRF.py:153-196
+ *
+ * The reference has no FFI for this path: its "plugin API" is the two nn.Module classes.  The
+ * Python mirror of those classes (localrf_b200/tensorf.py, localrf_b200/local_tensorfs.py) binds
+ * these entry points through ctypes; INTEGRATION.md shows the stub a maintainer of the reference
+ * would add.  Plain pointers and sizes only -- no torch types.
+ *
+ * All pointers are DEVICE pointers on the current CUDA device unless stated otherwise; all
+ * floating-point data is fp32; work is enqueued on `stream` and never synchronises the host.
+ * Every function returns LRF_OK (0) or a negative error code; lrf_last_error() gives the text.
+ *
+ * HBM layout of a field ("channel-last", one texel's components contiguous):
+ *     plane i : [H_i][W_i][C]     W_i = grid[matMode[i][0]], H_i = grid[matMode[i][1]]
+ *     line  i : [L_i][C]          L_i = grid[vecMode[i]]
+ *     matMode = {{0,1},{0,2},{1,2}}, vecMode = {2,1,0}          (models/tensorBase.py:274-275)
+ * This is exactly the memory of the reference's [1,C,H,W] / [1,C,L,1] parameters when they are
+ * allocated with torch.channels_last; lrf_repack_nchw_to_nhwc() converts a contiguous NCHW tensor.
+ * C = 8 (density) and 24 (appearance) per plane are the reference defaults (opt.py:117-119) and
+ * the only component counts built so far; app_dim = 27, featureC = 128, positional encodings 0.
+ */
+#ifndef LOCALRF_B200_H
+#define LOCALRF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRF_OK 0
+#define LRF_ERR_INVALID -1      /* bad argument (null pointer, size, unsupported configuration) */
+#define LRF_ERR_UNSUPPORTED -2  /* valid reference configuration that this build does not cover */
+#define LRF_ERR_CUDA -3         /* a CUDA runtime call failed */
+
+typedef struct CUstream_st *lrf_stream_t; /* == cudaStream_t */
+
+/* One radiance field (TensorVMSplit): the parameters TensorBase.forward reads.
+ * replaces: TensorVMSplit attributes, models/tensorBase.py:232-287, models/tensoRF.py:18-50 */
+typedef struct LrfField {
+  int32_t grid[3];            /* gridSize (x,y,z)                       tensorBase.py:322 */
+  float aabb[6];              /* aabb[0] = min xyz, aabb[1] = max xyz   tensorBase.py:259 */
+  int32_t n_dcomp;            /* density components per plane (8)       tensorBase.py:256 */
+  int32_t n_acomp;            /* appearance components per plane (24)   tensorBase.py:257 */
+  const float *dplane[3];     /* [H_i][W_i][n_dcomp] */
+  const float *dline[3];      /* [L_i][n_dcomp] */
+  const float *aplane[3];     /* [H_i][W_i][n_acomp] */
+  const float *aline[3];      /* [L_i][n_acomp] */
+  int32_t app_dim;            /* 27 */
+  const float *basis;         /* basis_mat.weight [app_dim][3*n_acomp]  tensoRF.py:25-27 */
+  int32_t featureC;           /* 128 */
+  int32_t fea_pe, view_pe;    /* 0, 0 */
+  const float *w1, *b1;       /* renderModule.mlp[0]      [featureC][app_dim], [featureC] */
+  const float *w2, *b2;       /* renderModule.mlp[2]      [featureC][featureC], [featureC] */
+  const float *w3, *b3;       /* renderModule.mlp_view[0] [3][featureC+3], [3] */
+  const float *alpha_vol;     /* AlphaGridMask.alpha_volume [D][H][W], or NULL  tensorBase.py:38-62 */
+  int32_t alpha_dims[3];      /* D, H, W */
+  float alpha_aabb[6];
+  float density_shift;        /* tensorBase.py:263 */
+  float distance_scale;       /* tensorBase.py:265 */
+  float weight_thres;         /* rayMarch_weight_thres, tensorBase.py:266 */
+  int32_t act;                /* 0 = softplus, 1 = relu                 tensorBase.py:495-499 */
+  const float *z_vals;        /* [n_samples] per-batch distance table (tensorBase.py:419-437);
+                                 the host builds it (it owns the RNG of the train-mode jitter) */
+  int32_t n_samples;          /* S = 2*(nSamples/6) */
+} LrfField;
+
+/* One ray batch.  Either explicit rays (TensorBase.forward's rays_chunk) or ray ids + cameras
+ * (LocalTensorfs.forward; the kernel then generates origin/direction itself).
+ * replaces: local_tensorfs.py:397-456 (ids2pixel, get_ray_directions_*, cam2rf, get_rays_lean) */
+typedef struct LrfBatch {
+  int64_t n_rays;
+  const float *rays;          /* [n_rays][6] (o, d) or NULL -> generate from the fields below */
+  const int64_t *ray_ids;     /* [n_rays]  col = id % W, row = (id / W) % H   local_tensorfs.py:23-29 */
+  int32_t W, H;
+  int32_t fov360;             /* 1: get_ray_directions_360, 0: get_ray_directions_lean */
+  float focal, cx, cy;        /* LocalTensorfs.focal(W), .center(W,H)   local_tensorfs.py:377-380 */
+  const float *intrinsics;    /* optional DEVICE [3] = {focal, cx, cy}; overrides the three values
+                                 above so learnable intrinsics never round-trip through the host */
+  const float *cam2world;     /* [n_views][3][4] */
+  int64_t n_views;            /* ray r uses view r / (n_rays / n_views)  local_tensorfs.py:437 */
+  const float *world2rf;      /* DEVICE [3] added to the camera translation (NULL = 0)  local_tensorfs.py:428 */
+  const float *blend;         /* per-view blending weight of THIS field: blend[v*blend_stride], or
+                                 NULL for weight 1                       local_tensorfs.py:438,452 */
+  int64_t blend_stride;
+  const float *exposure;      /* [n_views][3][3] or NULL; applied when `finalize` local_tensorfs.py:481-496 */
+  int32_t accumulate;         /* 0: rgb/depth = w*result; 1: rgb/depth += w*result  (:467-474) */
+  int32_t finalize;           /* 1: apply exposure (if any) and clamp(0,1) to rgb   (:481-497) */
+  int32_t white_bg;           /* tensorBase.py:633-634 (the caller resolves the train-mode coin) */
+  float floater_thresh;       /* tensorBase.py:617-620 */
+} LrfBatch;
+
+typedef struct LrfOutputs {
+  float *rgb;                 /* [n_rays][3] */
+  float *depth;               /* [n_rays] */
+  float *weights;             /* optional [n_rays][n_samples]: final per-sample weights of this field */
+  float *directions;          /* optional [n_rays][3]: camera-space directions (ray-generation mode) */
+  unsigned long long *stats;  /* optional [2]: += {density samples marched, appearance samples shaded} */
+} LrfOutputs;
+
+int lrf_version(void);
+const char *lrf_last_error(void);
+
+/* Device bytes of the per-field "prepared" block (folded / re-laid-out MLP weights). */
+size_t lrf_prepared_bytes(void);
+/* Builds the prepared block from the field's current MLP / basis weights.  Call again whenever
+ * those parameters change (every optimiser step while training). */
+int lrf_field_prepare(const LrfField *field, void *prepared, lrf_stream_t stream);
+
+/* The hot path: one fused launch per (field, ray batch).
+ * replaces: TensorBase.forward (tensorBase.py:567-636) + the per-field body of
+ * LocalTensorfs.forward's chunk loop (local_tensorfs.py:451-474) + :481-497 when finalize. */
+int lrf_render(const LrfField *field, const void *prepared, const LrfBatch *batch,
+               const LrfOutputs *out, lrf_stream_t stream);
+
+/* compute_densityfeature (tensoRF.py:112-151): xyz_norm [M][3] in [-1,1]^3 -> out [M] */
+int lrf_density_feature(const LrfField *field, const float *xyz_norm, int64_t M, float *out,
+                        lrf_stream_t stream);
+/* compute_appfeature (tensoRF.py:153-196): xyz_norm [M][3] -> out [M][app_dim] */
+int lrf_app_feature(const LrfField *field, const float *xyz_norm, int64_t M, float *out,
+                    lrf_stream_t stream);
+
+/* [C][H][W] (contiguous NCHW parameter of the reference) -> [H][W][C] */
+int lrf_repack_nchw_to_nhwc(const float *src, float *dst, int32_t C, int32_t H, int32_t W,
+                            lrf_stream_t stream);
+
+/* Launch configuration used by lrf_render on this device (for the bench's roofline record). */
+int lrf_launch_info(int32_t *n_sms, int32_t *threads_per_cta, int32_t *smem_bytes_per_cta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOCALRF_B200_H */

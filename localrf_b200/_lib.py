@@ -1,0 +1,138 @@
+"""ctypes binding of the C ABI (include/localrf_b200.h) + the in-tree nvcc build.
+
+The product path has NO fallback: if the shared library is missing or cannot be loaded,
+`lib()` raises.  Nothing here imports oracle/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_CSRC, "liblrf_b200.so")
+SOURCES = ["lrf_render.cu", "lrf_abi.cu"]
+HEADERS = ["lrf_common.cuh", os.path.join("..", "..", "include", "localrf_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+_fp = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+
+class LrfField(C.Structure):
+    _fields_ = [
+        ("grid", C.c_int32 * 3),
+        ("aabb", C.c_float * 6),
+        ("n_dcomp", C.c_int32), ("n_acomp", C.c_int32),
+        ("dplane", _vp * 3), ("dline", _vp * 3), ("aplane", _vp * 3), ("aline", _vp * 3),
+        ("app_dim", C.c_int32),
+        ("basis", _vp),
+        ("featureC", C.c_int32), ("fea_pe", C.c_int32), ("view_pe", C.c_int32),
+        ("w1", _vp), ("b1", _vp), ("w2", _vp), ("b2", _vp), ("w3", _vp), ("b3", _vp),
+        ("alpha_vol", _vp),
+        ("alpha_dims", C.c_int32 * 3),
+        ("alpha_aabb", C.c_float * 6),
+        ("density_shift", C.c_float), ("distance_scale", C.c_float), ("weight_thres", C.c_float),
+        ("act", C.c_int32),
+        ("z_vals", _vp),
+        ("n_samples", C.c_int32),
+    ]
+
+
+class LrfBatch(C.Structure):
+    _fields_ = [
+        ("n_rays", C.c_int64),
+        ("rays", _vp),
+        ("ray_ids", _vp),
+        ("W", C.c_int32), ("H", C.c_int32),
+        ("fov360", C.c_int32),
+        ("focal", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("intrinsics", _vp),
+        ("cam2world", _vp),
+        ("n_views", C.c_int64),
+        ("world2rf", _vp),
+        ("blend", _vp),
+        ("blend_stride", C.c_int64),
+        ("exposure", _vp),
+        ("accumulate", C.c_int32), ("finalize", C.c_int32), ("white_bg", C.c_int32),
+        ("floater_thresh", C.c_float),
+    ]
+
+
+class LrfOutputs(C.Structure):
+    _fields_ = [("rgb", _vp), ("depth", _vp), ("weights", _vp), ("directions", _vp),
+                ("stats", _vp)]
+
+
+EXPORTS = ["lrf_version", "lrf_last_error", "lrf_prepared_bytes", "lrf_field_prepare",
+           "lrf_render", "lrf_density_feature", "lrf_app_feature", "lrf_repack_nchw_to_nhwc",
+           "lrf_launch_info"]
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(os.path.join(_CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> localrf_b200/csrc/liblrf_b200.so"""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    env = dict(os.environ)
+    env.pop("CC", None); env.pop("CXX", None)  # the image's CC points at a gcc without libgomp
+    r = subprocess.run(cmd, cwd=_CSRC, capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout + r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (building it if sources are newer).  Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _stale():
+        try:
+            build()
+        except (RuntimeError, FileNotFoundError) as e:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    "localrf_b200: the CUDA library is not built and nvcc failed; there is no "
+                    f"CPU fallback ({e})") from e
+    L = C.CDLL(LIB_PATH)
+    L.lrf_version.restype = C.c_int
+    L.lrf_last_error.restype = C.c_char_p
+    L.lrf_prepared_bytes.restype = C.c_size_t
+    L.lrf_field_prepare.argtypes = [C.POINTER(LrfField), _vp, _vp]
+    L.lrf_render.argtypes = [C.POINTER(LrfField), _vp, C.POINTER(LrfBatch), C.POINTER(LrfOutputs), _vp]
+    L.lrf_density_feature.argtypes = [C.POINTER(LrfField), _vp, C.c_int64, _vp, _vp]
+    L.lrf_app_feature.argtypes = [C.POINTER(LrfField), _vp, C.c_int64, _vp, _vp]
+    L.lrf_repack_nchw_to_nhwc.argtypes = [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]
+    L.lrf_launch_info.argtypes = [C.POINTER(C.c_int32)] * 3
+    for name in EXPORTS:
+        getattr(L, name)  # AttributeError if the header and the library ever drift apart
+    _lib = L
+    return L
+
+
+class LrfError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().lrf_last_error().decode()
+        if rc == -2:
+            raise NotImplementedError(f"localrf_b200: {msg}")
+        if rc == -1:
+            raise ValueError(f"localrf_b200: {msg}")
+        raise LrfError(f"localrf_b200 (code {rc}): {msg}")

@@ -1,0 +1,236 @@
+// lrf_abi.cu -- the C ABI declared in include/localrf_b200.h (validation + launches).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/localrf_b200.h"
+#include "lrf_common.cuh"
+
+namespace lrf {
+size_t render_smem_bytes(int S, bool floater);
+int render_threads();
+cudaError_t launch_render(const FieldDev& F, const BatchDev& B, int n_sms, cudaStream_t stream);
+cudaError_t launch_prepare(const float* basis, const float* w1, const float* b1, const float* w2,
+                           const float* b2, const float* w3, const float* b3, float* prep,
+                           cudaStream_t stream);
+cudaError_t launch_density_feature(const FieldDev& F, const float* xyz, long long M, float* out,
+                                   cudaStream_t stream);
+cudaError_t launch_app_feature(const FieldDev& F, const float* basis, const float* xyz,
+                               long long M, float* out, cudaStream_t stream);
+cudaError_t launch_repack(const float* src, float* dst, int C, long long HW, cudaStream_t stream);
+}  // namespace lrf
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* a = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return LRF_ERR_CUDA;
+}
+
+struct DevInfo {
+  int n_sms = 0;
+  int max_smem = 0;
+  bool ok = false;
+};
+
+int device_info(DevInfo& d) {
+  static thread_local DevInfo cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev < 0 || dev >= 64) return fail(LRF_ERR_INVALID, "device index out of range");
+  if (!cache[dev].ok) {
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    cache[dev].n_sms = p.multiProcessorCount;
+    cache[dev].max_smem = (int)p.sharedMemPerBlockOptin;
+    cache[dev].ok = true;
+  }
+  d = cache[dev];
+  return LRF_OK;
+}
+
+// validates the parts of a field every entry point needs and fills the device-side view
+int make_field(const LrfField* f, bool need_mlp, bool need_table, const void* prepared,
+               lrf::FieldDev& F) {
+  if (!f) return fail(LRF_ERR_INVALID, "field is NULL");
+  if (f->n_dcomp != lrf::CD || f->n_acomp != lrf::CA)
+    return fail(LRF_ERR_UNSUPPORTED, "only density_n_comp=8 / appearance_n_comp=24 per plane are built");
+  for (int a = 0; a < 3; ++a) {
+    if (f->grid[a] < 2) return fail(LRF_ERR_INVALID, "gridSize must be >= 2 on every axis");
+    if (!(f->aabb[3 + a] > f->aabb[a])) return fail(LRF_ERR_INVALID, "aabb max must exceed aabb min");
+    F.g[a] = f->grid[a];
+    F.amin[a] = f->aabb[a];
+    F.ainv[a] = 2.0f / (f->aabb[3 + a] - f->aabb[a]);
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (!f->dplane[i] || !f->dline[i] || !f->aplane[i] || !f->aline[i])
+      return fail(LRF_ERR_INVALID, "plane/line pointer is NULL");
+    if (((uintptr_t)f->dplane[i] | (uintptr_t)f->dline[i] | (uintptr_t)f->aplane[i] |
+         (uintptr_t)f->aline[i]) & 15)
+      return fail(LRF_ERR_INVALID, "plane/line pointers must be 16-byte aligned");
+    F.dplane[i] = f->dplane[i]; F.dline[i] = f->dline[i];
+    F.aplane[i] = f->aplane[i]; F.aline[i] = f->aline[i];
+  }
+  F.prep = static_cast<const float*>(prepared);
+  F.alpha_vol = f->alpha_vol;
+  if (f->alpha_vol) {
+    for (int a = 0; a < 3; ++a) {
+      if (f->alpha_dims[a] < 1) return fail(LRF_ERR_INVALID, "alpha mask dims must be >= 1");
+      F.ad[a] = f->alpha_dims[a];
+      F.aamin[a] = f->alpha_aabb[a];
+      F.aainv[a] = 1.0f / (f->alpha_aabb[3 + a] - f->alpha_aabb[a]) * 2.0f;
+    }
+  } else {
+    for (int a = 0; a < 3; ++a) { F.ad[a] = 1; F.aamin[a] = 0.f; F.aainv[a] = 0.f; }
+  }
+  F.density_shift = f->density_shift;
+  F.distance_scale = f->distance_scale;
+  F.weight_thres = f->weight_thres;
+  if (f->act != 0 && f->act != 1) return fail(LRF_ERR_INVALID, "act must be 0 (softplus) or 1 (relu)");
+  F.act = f->act;
+  if (need_mlp) {
+    if (f->app_dim != lrf::APP_DIM || f->featureC != lrf::FC)
+      return fail(LRF_ERR_UNSUPPORTED, "only app_dim=27 / featureC=128 are built");
+    if (f->fea_pe != 0 || f->view_pe != 0)
+      return fail(LRF_ERR_UNSUPPORTED, "positional encodings (fea_pe/view_pe > 0) are not built yet");
+  }
+  F.z = f->z_vals;
+  F.S = f->n_samples;
+  if (need_table) {
+    if (!f->z_vals) return fail(LRF_ERR_INVALID, "z_vals is NULL");
+    if (f->n_samples < 2 || f->n_samples > 65535)
+      return fail(LRF_ERR_INVALID, "n_samples must be in [2, 65535]");
+  }
+  return LRF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lrf_version(void) { return 1; }
+
+const char* lrf_last_error(void) { return g_err; }
+
+size_t lrf_prepared_bytes(void) { return (size_t)lrf::PREP_FLOATS * sizeof(float); }
+
+int lrf_field_prepare(const LrfField* f, void* prepared, lrf_stream_t stream) {
+  if (!f || !prepared) return fail(LRF_ERR_INVALID, "field or prepared is NULL");
+  if ((uintptr_t)prepared & 15) return fail(LRF_ERR_INVALID, "prepared must be 16-byte aligned");
+  if (f->app_dim != lrf::APP_DIM || f->featureC != lrf::FC || f->n_acomp != lrf::CA)
+    return fail(LRF_ERR_UNSUPPORTED, "only app_dim=27 / featureC=128 / appearance_n_comp=24 are built");
+  if (f->fea_pe != 0 || f->view_pe != 0)
+    return fail(LRF_ERR_UNSUPPORTED, "positional encodings (fea_pe/view_pe > 0) are not built yet");
+  if (!f->basis || !f->w1 || !f->b1 || !f->w2 || !f->b2 || !f->w3 || !f->b3)
+    return fail(LRF_ERR_INVALID, "MLP / basis pointer is NULL");
+  cudaError_t e = lrf::launch_prepare(f->basis, f->w1, f->b1, f->w2, f->b2, f->w3, f->b3,
+                                      static_cast<float*>(prepared), (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "prepare_kernel");
+  return LRF_OK;
+}
+
+int lrf_render(const LrfField* f, const void* prepared, const LrfBatch* b, const LrfOutputs* o,
+               lrf_stream_t stream) {
+  if (!b || !o) return fail(LRF_ERR_INVALID, "batch or outputs is NULL");
+  if (!prepared) return fail(LRF_ERR_INVALID, "prepared is NULL (call lrf_field_prepare first)");
+  lrf::FieldDev F;
+  int rc = make_field(f, true, true, prepared, F);
+  if (rc != LRF_OK) return rc;
+  if (b->n_rays < 0) return fail(LRF_ERR_INVALID, "n_rays < 0");
+  if (b->n_rays == 0) return LRF_OK;
+  if (!o->rgb || !o->depth) return fail(LRF_ERR_INVALID, "rgb/depth output is NULL");
+  lrf::BatchDev B;
+  memset(&B, 0, sizeof(B));
+  B.n_rays = b->n_rays;
+  B.rays = b->rays;
+  B.rays_per_view = 0;
+  const bool per_view = b->blend || b->exposure || !b->rays;
+  if (per_view) {
+    if (b->n_views < 1 || b->n_rays % b->n_views != 0)
+      return fail(LRF_ERR_INVALID, "n_rays must be a positive multiple of n_views");
+    B.rays_per_view = b->n_rays / b->n_views;
+  }
+  if (!b->rays) {
+    if (!b->ray_ids || !b->cam2world) return fail(LRF_ERR_INVALID, "ray_ids/cam2world is NULL");
+    if (b->W < 1 || b->H < 1) return fail(LRF_ERR_INVALID, "W/H must be positive");
+    if (!b->fov360 && !b->intrinsics && !(b->focal != 0.0f))
+      return fail(LRF_ERR_INVALID, "focal must be non-zero");
+  }
+  B.ray_ids = reinterpret_cast<const long long*>(b->ray_ids);
+  B.W = b->W; B.H = b->H; B.fov360 = b->fov360;
+  B.focal = b->focal; B.cx = b->cx; B.cy = b->cy;
+  B.intrinsics = b->intrinsics;
+  B.c2w = b->cam2world;
+  B.w2rf = b->world2rf;
+  B.blend = b->blend;
+  B.blend_stride = b->blend_stride;
+  B.exposure = b->exposure;
+  B.accumulate = b->accumulate; B.finalize = b->finalize; B.white_bg = b->white_bg;
+  B.floater_thresh = b->floater_thresh;
+  B.rgb = o->rgb; B.depth = o->depth; B.weights = o->weights;
+  B.dirs = b->rays ? nullptr : o->directions;
+  B.stats = o->stats;
+  DevInfo d;
+  rc = device_info(d);
+  if (rc != LRF_OK) return rc;
+  const size_t smem = lrf::render_smem_bytes(F.S, B.floater_thresh > 0.0f);
+  if ((long long)smem > d.max_smem)
+    return fail(LRF_ERR_UNSUPPORTED, "sample table too long for the shared-memory budget");
+  cudaError_t e = lrf::launch_render(F, B, d.n_sms, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "render_kernel");
+  return LRF_OK;
+}
+
+int lrf_density_feature(const LrfField* f, const float* xyz, int64_t M, float* out,
+                        lrf_stream_t stream) {
+  lrf::FieldDev F;
+  int rc = make_field(f, false, false, nullptr, F);
+  if (rc != LRF_OK) return rc;
+  if (M < 0 || (M > 0 && (!xyz || !out))) return fail(LRF_ERR_INVALID, "bad xyz/out/M");
+  cudaError_t e = lrf::launch_density_feature(F, xyz, M, out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "density_feature_kernel");
+  return LRF_OK;
+}
+
+int lrf_app_feature(const LrfField* f, const float* xyz, int64_t M, float* out,
+                    lrf_stream_t stream) {
+  lrf::FieldDev F;
+  int rc = make_field(f, false, false, nullptr, F);
+  if (rc != LRF_OK) return rc;
+  if (f->app_dim != lrf::APP_DIM) return fail(LRF_ERR_UNSUPPORTED, "only app_dim=27 is built");
+  if (!f->basis) return fail(LRF_ERR_INVALID, "basis is NULL");
+  if (M < 0 || (M > 0 && (!xyz || !out))) return fail(LRF_ERR_INVALID, "bad xyz/out/M");
+  cudaError_t e = lrf::launch_app_feature(F, f->basis, xyz, M, out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "app_feature_kernel");
+  return LRF_OK;
+}
+
+int lrf_repack_nchw_to_nhwc(const float* src, float* dst, int32_t C, int32_t H, int32_t W,
+                            lrf_stream_t stream) {
+  if (!src || !dst || C < 1 || H < 1 || W < 1) return fail(LRF_ERR_INVALID, "bad repack arguments");
+  cudaError_t e = lrf::launch_repack(src, dst, C, (long long)H * W, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "repack_kernel");
+  return LRF_OK;
+}
+
+int lrf_launch_info(int32_t* n_sms, int32_t* threads_per_cta, int32_t* smem_bytes_per_cta) {
+  DevInfo d;
+  int rc = device_info(d);
+  if (rc != LRF_OK) return rc;
+  if (n_sms) *n_sms = d.n_sms;
+  if (threads_per_cta) *threads_per_cta = lrf::render_threads();
+  if (smem_bytes_per_cta) *smem_bytes_per_cta = (int32_t)lrf::render_smem_bytes(344, false);
+  return LRF_OK;
+}
+
+}  // extern "C"

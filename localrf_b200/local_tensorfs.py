@@ -1,0 +1,418 @@
+"""Host-side mirror of the reference's scene model (local_tensorfs.py:31-499).
+
+`LocalTensorfs` keeps the reference's constructor kwargs, attributes, `state_dict` key set
+(`blending_weights, init_focal, focal_offset, center_rel, r_c2w.i, t_c2w.i, exposure.i, world2rf.k,
+tensorfs.k.*`) and method signatures, so the reference's train.py / renderer.py can import it
+unchanged.  `forward` is the B200 path: every active field is ONE fused kernel launch over the
+whole ray batch (ray generation, march, shading, blend accumulation; exposure + clamp ride on the
+last field's launch).  Differences that are deliberate:
+
+  * fields are never parked on the CPU (180 GB of HBM holds every field of a scene); the
+    reference's CPU<->GPU shuffle (local_tensorfs.py:132,432-434,476-479) has no equivalent;
+  * `chunk` does not bound memory any more (the kernel materialises nothing per sample); it is
+    honoured only in train mode, where each chunk draws its own jitter like the reference;
+  * `sixD_to_mtx` uses the per-view cross product for every batch size (see utils.py).
+"""
+import ctypes as C
+import math
+import re
+
+import torch
+
+from . import _lib
+from .tensorf import AlphaGridMask, TensorVMSplit, _ptr, _require_cuda, _stream
+from .utils import N_to_reso, mtx_to_sixD, sixD_to_mtx
+
+
+def ids2pixel_view(W, H, ids):
+    """local_tensorfs.py:14-21."""
+    return ids % W, (ids // W) % H, ids // (W * H)
+
+
+def ids2pixel(W, H, ids):
+    """local_tensorfs.py:23-29."""
+    return ids % W, (ids // W) % H
+
+
+class LocalTensorfs(torch.nn.Module):
+    """Self-calibrating sequence of local radiance fields."""
+
+    def __init__(self, fov, n_init_frames, n_overlap, WH, n_iters_per_frame, n_iters_reg,
+                 lr_R_init, lr_t_init, lr_i_init, lr_exposure_init, rf_lr_init, rf_lr_basis,
+                 lr_decay_target_ratio, N_voxel_list, update_AlphaMask_list, camera_prior, device,
+                 lr_upsample_reset, **tensorf_args):
+        super().__init__()
+        self.fov = fov
+        self.n_init_frames = n_init_frames
+        self.n_overlap = n_overlap
+        self.W, self.H = WH
+        self.n_iters_per_frame = n_iters_per_frame
+        self.n_iters_reg_per_frame = n_iters_reg
+        self.lr_R_init, self.lr_t_init = lr_R_init, lr_t_init
+        self.lr_i_init, self.lr_exposure_init = lr_i_init, lr_exposure_init
+        self.rf_lr_init, self.rf_lr_basis = rf_lr_init, rf_lr_basis
+        self.lr_decay_target_ratio = lr_decay_target_ratio
+        self.N_voxel_per_frame_list = N_voxel_list
+        self.update_AlphaMask_per_frame_list = update_AlphaMask_list
+        self.device = torch.device(device)
+        self.camera_prior = camera_prior
+        self.tensorf_args = tensorf_args
+        self.is_refining = False
+        self.lr_upsample_reset = lr_upsample_reset
+
+        self.lr_factor = 1
+        self.regularize = True
+        self.n_iters_reg = self.n_iters_reg_per_frame
+        self.n_iters = self.n_iters_per_frame
+        self.update_AlphaMask_list = update_AlphaMask_list
+        self.N_voxel_list = N_voxel_list
+
+        # per-frame pose / exposure parameters, one optimiser each (local_tensorfs.py:85-92)
+        self.r_c2w = torch.nn.ParameterList()
+        self.t_c2w = torch.nn.ParameterList()
+        self.exposure = torch.nn.ParameterList()
+        self.r_optimizers, self.t_optimizers, self.exp_optimizers = [], [], []
+        self.pose_linked_rf = []
+        self.blending_weights = torch.nn.Parameter(
+            torch.ones([1, 1], device=self.device), requires_grad=False)
+        for _ in range(n_init_frames):
+            self.append_frame()
+
+        if self.camera_prior is not None:
+            focal = self.camera_prior["transforms"]["fl_x"] * self.W / self.camera_prior["transforms"]["w"]
+        else:
+            focal = self.W / math.tan(fov * math.pi / 180 / 2) / 2
+        self.init_focal = torch.nn.Parameter(torch.Tensor([focal]).to(self.device))
+        self.focal_offset = torch.nn.Parameter(torch.ones(1, device=device))
+        self.center_rel = torch.nn.Parameter(0.5 * torch.ones(2, device=device))
+        if lr_i_init > 0:
+            self.intrinsic_optimizer = torch.optim.Adam(
+                [self.focal_offset, self.center_rel], betas=(0.9, 0.99), lr=self.lr_i_init)
+
+        # radiance fields
+        self.tensorfs = torch.nn.ParameterList()
+        self.rf_iter = []
+        self.world2rf = torch.nn.ParameterList()
+        self.append_rf()
+
+    # ---------------------------------------------------------------------------------------------
+    # progressive-schedule bookkeeping (host side; local_tensorfs.py:116-290)
+    # ---------------------------------------------------------------------------------------------
+    def append_rf(self, n_added_frames=1):
+        """Opens a new field centred at the latest camera and cross-fades the blending rows of the
+        last `n_overlap` frames from the previous field to the new one (:116-146)."""
+        self.is_refining = False
+        if len(self.tensorfs) > 0:
+            n_ov = min(n_added_frames, self.n_overlap, self.blending_weights.shape[0] - 1)
+            ramp = 1 / n_ov + torch.arange(0, 1, 1 / n_ov)
+            bw = self.blending_weights.detach().clone()
+            bw[-n_ov:, -1] = (1 - ramp).to(bw)
+            new_col = torch.zeros_like(bw[:, :1])
+            new_col[-n_ov:, 0] = ramp.to(bw)
+            self.blending_weights = torch.nn.Parameter(torch.cat([bw, new_col], dim=1),
+                                                       requires_grad=False)
+            world2rf = -self.t_c2w[-1].clone().detach()
+            # (the reference parks the previous field on the CPU here; it stays resident)
+        else:
+            world2rf = torch.zeros(3, device=self.device)
+        self.tensorfs.append(TensorVMSplit(device=self.device, **self.tensorf_args))
+        self.world2rf.append(world2rf.clone().detach())
+        self.rf_iter.append(0)
+        groups = self.tensorfs[-1].get_optparam_groups(self.rf_lr_init, self.rf_lr_basis)
+        self.rf_optimizer = torch.optim.Adam(groups, betas=(0.9, 0.99))
+
+    def append_frame(self):
+        """Adds one frame's pose / exposure parameters, initialised from the previous frame
+        (:148-177)."""
+        if len(self.r_c2w) == 0:
+            self.r_c2w.append(torch.eye(3, 2, device=self.device))
+            self.t_c2w.append(torch.zeros(3, device=self.device))
+            self.pose_linked_rf.append(0)
+        else:
+            prev_r = self.r_c2w[-1].clone().detach()[None]
+            self.r_c2w.append(mtx_to_sixD(sixD_to_mtx(prev_r))[0])
+            self.t_c2w.append(self.t_c2w[-1].clone().detach())
+            self.blending_weights = torch.nn.Parameter(
+                torch.cat([self.blending_weights, self.blending_weights[-1:, :]], dim=0),
+                requires_grad=False)
+            self.pose_linked_rf.append(int(torch.nonzero(self.blending_weights[-1, :])[0]))
+        self.exposure.append(torch.eye(3, 3, device=self.device))
+
+        if self.camera_prior is not None:
+            idx = len(self.r_c2w) - 1
+            rel_pose = self.camera_prior["rel_poses"][idx]
+            last_r = sixD_to_mtx(self.r_c2w[-1].clone().detach()[None])[0]
+            self.r_c2w[-1] = last_r @ rel_pose[:3, :3]
+            self.t_c2w[-1].data += last_r @ rel_pose[:3, 3]
+
+        adam = lambda p, lr: torch.optim.Adam([p], betas=(0.9, 0.99), lr=lr)
+        self.r_optimizers.append(adam(self.r_c2w[-1], self.lr_R_init))
+        self.t_optimizers.append(adam(self.t_c2w[-1], self.lr_t_init))
+        self.exp_optimizers.append(adam(self.exposure[-1], self.lr_exposure_init))
+
+    def _live_pose_ids(self):
+        """Frames whose pose is still optimised: linked to the newest field, within its budget."""
+        newest = len(self.rf_iter) - 1
+        if self.rf_iter[-1] >= self.n_iters:
+            return []
+        return [i for i, rf in enumerate(self.pose_linked_rf) if rf == newest]
+
+    def optimizer_step_poses_only(self, loss):
+        live = self._live_pose_ids()
+        for i in live:
+            self.r_optimizers[i].zero_grad()
+            self.t_optimizers[i].zero_grad()
+        loss.backward()
+        for i in live:
+            self.r_optimizers[i].step()
+            self.t_optimizers[i].step()
+
+    def optimizer_step(self, loss, optimize_poses):
+        """One optimisation step + the schedule events it triggers (:193-290)."""
+        it = self.rf_iter[-1]
+        if it == 0:
+            self.lr_factor = 1
+            self.n_iters = self.n_iters_per_frame
+            self.n_iters_reg = self.n_iters_reg_per_frame
+        elif it == 1:
+            n_train = (self.blending_weights[:, -1] > 0).sum()
+            self.n_iters = int(self.n_iters_per_frame * n_train)
+            self.n_iters_reg = int(self.n_iters_reg_per_frame * n_train)
+            self.lr_factor = self.lr_decay_target_ratio ** (1 / self.n_iters)
+            self.N_voxel_list = {int(k * n_train): v for k, v in self.N_voxel_per_frame_list.items()}
+            self.update_AlphaMask_list = [int(u * n_train) for u in self.update_AlphaMask_per_frame_list]
+        self.regularize = self.rf_iter[-1] < self.n_iters_reg
+
+        def decay(opt):
+            for group in opt.param_groups:
+                group["lr"] *= self.lr_factor
+
+        live = self._live_pose_ids()
+        for i in live:
+            if optimize_poses:
+                decay(self.r_optimizers[i]); decay(self.t_optimizers[i])
+                self.r_optimizers[i].zero_grad(); self.t_optimizers[i].zero_grad()
+            if self.lr_exposure_init > 0:
+                decay(self.exp_optimizers[i])
+                self.exp_optimizers[i].zero_grad()
+        tune_intrinsics = (self.lr_i_init > 0 and self.blending_weights.shape[1] == 1
+                           and self.is_refining)
+        if tune_intrinsics:
+            decay(self.intrinsic_optimizer)
+            self.intrinsic_optimizer.zero_grad()
+        self.rf_optimizer.zero_grad()
+
+        loss.backward()
+
+        self.rf_optimizer.step()
+        if self.is_refining:
+            decay(self.rf_optimizer)
+
+        if self.rf_iter[-1] in self.N_voxel_list:          # raise the grid resolution
+            reso = N_to_reso(self.N_voxel_list[self.rf_iter[-1]], self.tensorfs[-1].aabb)
+            self.tensorfs[-1].upsample_volume_grid(reso)
+            if self.lr_upsample_reset:
+                print("reset lr to initial")
+                groups = self.tensorfs[-1].get_optparam_groups(self.rf_lr_init, self.rf_lr_basis)
+                self.rf_optimizer = torch.optim.Adam(groups, betas=(0.9, 0.99))
+        if self.rf_iter[-1] in self.update_AlphaMask_list:  # rebuild the occupancy mask
+            self.tensorfs[-1].updateAlphaMask(tuple((self.tensorfs[-1].gridSize / 2).int()))
+
+        for i in live:
+            if optimize_poses:
+                self.r_optimizers[i].step(); self.t_optimizers[i].step()
+            if self.lr_exposure_init > 0:
+                self.exp_optimizers[i].step()
+        if tune_intrinsics:
+            self.intrinsic_optimizer.step()
+        if self.is_refining:
+            self.rf_iter[-1] += 1
+        return self.rf_iter[-1] >= self.n_iters - 1       # can_add_rf
+
+    # ---------------------------------------------------------------------------------------------
+    def get_cam2world(self, view_ids=None, starting_id=0):
+        """[V,3,4] camera-to-world matrices from the 6-D rotations and translations (:292-299)."""
+        if view_ids is not None:
+            ids = view_ids.tolist() if torch.is_tensor(view_ids) else list(view_ids)
+            r = torch.stack([self.r_c2w[i] for i in ids], dim=0)
+            t = torch.stack([self.t_c2w[i] for i in ids], dim=0)
+        else:
+            r = torch.stack(list(self.r_c2w[starting_id:]), dim=0)
+            t = torch.stack(list(self.t_c2w[starting_id:]), dim=0)
+        return torch.cat([sixD_to_mtx(r), t[..., None]], dim=-1)
+
+    def get_kwargs(self):
+        kwargs = {
+            "camera_prior": None, "fov": self.fov, "n_init_frames": self.n_init_frames,
+            "n_overlap": self.n_overlap, "WH": (self.W, self.H),
+            "n_iters_per_frame": self.n_iters_per_frame, "n_iters_reg": self.n_iters_reg_per_frame,
+            "lr_R_init": self.lr_R_init, "lr_t_init": self.lr_t_init, "lr_i_init": self.lr_i_init,
+            "lr_exposure_init": self.lr_exposure_init, "rf_lr_init": self.rf_lr_init,
+            "rf_lr_basis": self.rf_lr_basis, "lr_decay_target_ratio": self.lr_decay_target_ratio,
+            "N_voxel_list": self.N_voxel_per_frame_list,
+            "update_AlphaMask_list": self.update_AlphaMask_per_frame_list,
+            "lr_upsample_reset": self.lr_upsample_reset,
+        }
+        kwargs.update(self.tensorfs[0].get_kwargs())
+        return kwargs
+
+    def save(self, path):
+        torch.save({"kwargs": self.get_kwargs(), "state_dict": self.state_dict()}, path)
+
+    def load(self, state_dict):
+        """Rebuilds the frame / field structure from the key names, then loads (:331-356)."""
+        n_frames = 0
+        for key in state_dict:
+            if re.fullmatch(r"r_c2w.[0-9]*", key):
+                n_frames += 1
+            if re.fullmatch(r"tensorfs.[1-9][0-9]*.density_plane.0", key):
+                plane0 = state_dict[key]
+                line0 = state_dict[key[: -len("density_plane.0")] + "density_line.0"]
+                self.tensorf_args["gridSize"] = [plane0.shape[2], plane0.shape[3], line0.shape[2]]
+                self.append_rf()
+        for i, rf in enumerate(self.tensorfs):
+            if f"tensorfs.{i}.alphaMask.aabb" in state_dict:
+                vol = state_dict[f"tensorfs.{i}.alphaMask.alpha_volume"].to(self.device)
+                aabb = state_dict[f"tensorfs.{i}.alphaMask.aabb"].to(self.device)
+                rf.alphaMask = AlphaGridMask(self.device, aabb, vol)
+        for _ in range(n_frames - len(self.r_c2w)):
+            self.append_frame()
+        self.blending_weights = torch.nn.Parameter(
+            torch.ones_like(state_dict["blending_weights"]), requires_grad=False)
+        self.load_state_dict(state_dict)
+
+    def get_dist_to_last_rf(self):
+        return torch.norm(self.t_c2w[-1] + self.world2rf[-1])
+
+    def get_reg_loss(self, tvreg, TV_weight_density, TV_weight_app, L1_weight_inital):
+        tv_loss, l1_loss = 0, 0
+        if self.rf_iter[-1] < self.n_iters:
+            anneal = self.lr_factor ** self.rf_iter[-1]
+            if TV_weight_density > 0:
+                tv_loss += self.tensorfs[-1].TV_loss_density(tvreg).mean() * (TV_weight_density * anneal)
+            if TV_weight_app > 0:
+                tv_loss += self.tensorfs[-1].TV_loss_app(tvreg).mean() * (TV_weight_app * anneal)
+            if L1_weight_inital > 0:
+                l1_loss += self.tensorfs[-1].density_L1() * L1_weight_inital
+        return tv_loss, l1_loss
+
+    def focal(self, W):
+        return self.init_focal * self.focal_offset * W / self.W
+
+    def center(self, W, H):
+        return torch.Tensor([W, H]).to(self.center_rel) * self.center_rel
+
+    # ---------------------------------------------------------------------------------------------
+    # the hot path (local_tensorfs.py:382-499)
+    # ---------------------------------------------------------------------------------------------
+    def _exposure_for(self, view_ids, test_id):
+        """Per-view 3x3 exposure; held-out frames average their neighbours (:481-493)."""
+        stacked = torch.stack(list(self.exposure), dim=0)
+        if not test_id:
+            return stacked[view_ids]
+        stacked = stacked.clone().detach()
+        lo = torch.clamp(view_ids - 1, min=0)
+        lo[lo == view_ids] = 1
+        hi = torch.clamp(view_ids + 1, max=len(self.exposure) - 1)
+        hi[lo == view_ids] = len(self.exposure) - 2
+        return (stacked[lo] + stacked[hi]) / 2
+
+    def forward(self, ray_ids, view_ids, W, H, white_bg=True, is_train=True, cam2world=None,
+                world2rf=None, blending_weights=None, chunk=16384, test_id=False,
+                floater_thresh=0, stats=None):
+        """-> (rgbs [N,3], depth_maps [N], directions [N,3], ij [N,2]) like the reference."""
+        _require_cuda(ray_ids, "ray_ids")
+        dev = ray_ids.device
+        n = ray_ids.shape[0]
+        n_views = view_ids.shape[0]
+        if n % n_views != 0:
+            raise ValueError("ray_ids must hold the same number of rays for every view")
+        i, j = ids2pixel(W, H, ray_ids)
+        ij = torch.stack([i, j], dim=-1)
+
+        if blending_weights is None:
+            blending_weights = self.blending_weights[view_ids].clone()
+        else:
+            blending_weights = blending_weights.to(dev, torch.float32).clone()
+        if cam2world is None:
+            cam2world = self.get_cam2world(view_ids)
+        if world2rf is None:
+            world2rf = self.world2rf
+        if is_train:                                   # one field trains at a time (:411-416)
+            blending_weights[:, -1] = 1
+            blending_weights[:, :-1] = 0
+            active = [len(self.tensorfs) - 1]
+        else:
+            active = torch.nonzero(blending_weights.sum(dim=0))[:, 0].tolist()
+        if len(active) == 0:
+            print("****** No valid RF")
+            ones = torch.ones_like(ray_ids).float()
+            return torch.ones([n, 3], device=dev), ones, torch.zeros(n, 3, device=dev), ij
+
+        grads = [cam2world, self.init_focal, self.focal_offset, self.center_rel]
+        for k in active:
+            grads += list(self.tensorfs[k].parameters())
+        self.tensorfs[active[0]]._check_no_autograd(*grads)
+
+        cam2world = cam2world.detach().to(dev, torch.float32).contiguous()
+        blend = blending_weights.detach().contiguous()
+        fov360 = self.fov == 360
+        intr = torch.cat([self.focal(W).detach().reshape(1),
+                          self.center(W, H).detach().reshape(2)]).to(dev, torch.float32).contiguous()
+        ids = ray_ids.detach().to(torch.int64).contiguous()
+        exposure = None
+        if self.lr_exposure_init > 0:
+            exposure = self._exposure_for(view_ids, test_id).detach().to(dev, torch.float32).contiguous()
+
+        rgbs = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        depth = torch.empty(n, dtype=torch.float32, device=dev)
+        directions = torch.empty(n, 3, dtype=torch.float32, device=dev)
+
+        # train mode: the reference draws fresh jitter per chunk; eval has no randomness, so the
+        # whole batch is one launch per field.  Chunks are kept on view boundaries (the kernel
+        # derives a ray's view from its position in the launch).
+        per_view = n // n_views
+        budget = max(chunk // len(active), 1)
+        if is_train and n > budget:
+            chunk = max(per_view, (budget // per_view) * per_view)
+        else:
+            chunk = n
+        with torch.cuda.device(dev):
+            stream = _stream(dev)
+            for lo in range(0, n, chunk):
+                hi = min(lo + chunk, n)
+                v_lo, v_hi = lo // per_view, (hi + per_view - 1) // per_view
+                for pos, k in enumerate(active):
+                    rf = self.tensorfs[k]
+                    if rf.basis_mat.weight.device != dev:
+                        rf.to(dev)
+                    z = rf.sample_table(is_train, -1, dev)
+                    fs, keep = rf._field_struct(z)
+                    prep = rf.prepare(fs)
+                    w2rf = world2rf[k].detach().to(dev, torch.float32).contiguous()
+                    b = _lib.LrfBatch()
+                    b.n_rays = hi - lo
+                    b.ray_ids = ids.data_ptr() + 8 * lo
+                    b.W, b.H = int(W), int(H)
+                    b.fov360 = int(fov360)
+                    b.intrinsics = intr.data_ptr()
+                    b.cam2world = cam2world.data_ptr() + 48 * v_lo
+                    b.n_views = v_hi - v_lo
+                    b.world2rf = w2rf.data_ptr()
+                    b.blend = blend.data_ptr() + 4 * (v_lo * blend.shape[1] + k)
+                    b.blend_stride = blend.shape[1]
+                    b.accumulate = int(pos > 0)
+                    b.finalize = int(pos == len(active) - 1)
+                    if exposure is not None:
+                        b.exposure = exposure.data_ptr() + 36 * v_lo
+                    b.white_bg = int(bool(white_bg) or bool(is_train and torch.rand((1,)) < 0.5))
+                    b.floater_thresh = float(floater_thresh)
+                    o = _lib.LrfOutputs()
+                    o.rgb = rgbs.data_ptr() + 12 * lo
+                    o.depth = depth.data_ptr() + 4 * lo
+                    o.directions = directions.data_ptr() + 12 * lo
+                    if stats is not None:
+                        o.stats = stats.data_ptr()
+                    _lib.check(_lib.lib().lrf_render(C.byref(fs), _ptr(prep), C.byref(b),
+                                                     C.byref(o), stream))
+        return rgbs, depth, directions, ij

@@ -1,0 +1,509 @@
+"""Host-side mirror of the reference's radiance-field modules, backed by the fused CUDA kernel.
+
+Mirrors (same class names, constructor kwargs, attributes, `state_dict` keys and method
+signatures):
+
+    AlphaGridMask             models/tensorBase.py:38-62
+    MLPRender_Fea_late_view   models/tensorBase.py:97-135      (parameter container only)
+    TensorBase                models/tensorBase.py:231-636
+    TensorVMSplit             models/tensoRF.py:10-277
+
+`forward`, `compute_densityfeature` and `compute_appfeature` run through the C ABI
+(include/localrf_b200.h); there is no PyTorch or CPU fallback for them.  The remaining methods are
+host-side bookkeeping off the per-batch path (grid upsampling, alpha-mask rebuild, regularisers,
+optimiser groups) and are written with stock torch ops.
+
+B200-specific layout: plane/line parameters keep the reference's logical shapes
+([1,C,H,W] / [1,C,L,1]) and names, but are allocated in torch.channels_last memory format, i.e.
+physically [H][W][C] / [L][C] -- one texel's components are one 32-byte (density) or 96-byte
+(appearance) contiguous run, which is what the kernel gathers.
+"""
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+MAT_MODE = ((0, 1), (0, 2), (1, 2))   # models/tensorBase.py:274
+VEC_MODE = (2, 1, 0)                  # models/tensorBase.py:275
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _cl(t):
+    """channels_last view/copy of a [1,C,H,W] tensor."""
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"localrf_b200: {what} is on {t.device}; the render path runs only on a CUDA device "
+            "(there is no CPU fallback)")
+
+
+class AlphaGridMask(torch.nn.Module):
+    """models/tensorBase.py:38-62 -- binary occupancy volume, trilinearly sampled."""
+
+    def __init__(self, device, aabb, alpha_volume):
+        super().__init__()
+        self.device = device
+        self.aabb = torch.nn.Parameter(aabb.to(device), requires_grad=False)
+        self.aabbSize = self.aabb[1] - self.aabb[0]
+        self.invgridSize = torch.nn.Parameter(1.0 / self.aabbSize * 2, requires_grad=False)
+        vol = alpha_volume.view(1, 1, *alpha_volume.shape[-3:])
+        self.alpha_volume = torch.nn.Parameter(vol.to(device), requires_grad=False)
+        d, h, w = vol.shape[-3:]
+        self.gridSize = torch.LongTensor([w, h, d]).to(device)
+
+    def normalize_coord(self, xyz_sampled):
+        return (xyz_sampled - self.aabb[0]) * self.invgridSize - 1
+
+    def sample_alpha(self, xyz_sampled):
+        # off the per-batch path (used by compute_alpha / filtering); the render kernel has its
+        # own fused lookup
+        grid = self.normalize_coord(xyz_sampled).view(1, -1, 1, 1, 3)
+        return F.grid_sample(self.alpha_volume, grid, align_corners=True).view(-1)
+
+    def to(self, device):
+        self.device = torch.device(device)
+        return super().to(device)
+
+
+class MLPRender_Fea_late_view(torch.nn.Module):
+    """models/tensorBase.py:97-135 -- holds mlp[0], mlp[2], mlp_view[0] (same state_dict keys).
+
+    Inside TensorBase.forward the MLP is evaluated by the fused kernel; calling this module
+    directly evaluates it with torch ops (used by tests and by code that shades points itself).
+    """
+
+    def __init__(self, inChanel, viewpe=6, feape=6, featureC=128):
+        super().__init__()
+        self.in_mlpC = inChanel * (1 + 2 * feape)
+        self.in_view = 3 * (1 + 2 * viewpe)
+        self.viewpe, self.feape = viewpe, feape
+        self.mlp = torch.nn.Sequential(
+            torch.nn.Linear(self.in_mlpC, featureC), torch.nn.ReLU(inplace=True),
+            torch.nn.Linear(featureC, featureC), torch.nn.ReLU(inplace=True))
+        self.mlp_view = torch.nn.Sequential(torch.nn.Linear(featureC + self.in_view, 3))
+        torch.nn.init.constant_(self.mlp_view[-1].bias, 0)
+
+    @staticmethod
+    def _pe(x, n_freq):
+        bands = 2.0 ** torch.arange(n_freq, device=x.device, dtype=torch.float32)
+        ang = (x[..., None] * bands).reshape(*x.shape[:-1], -1)
+        return torch.cat([ang.sin(), ang.cos()], dim=-1)
+
+    def forward(self, pts, viewdirs, features, refine):
+        x = features
+        if self.feape > 0:
+            extra = self._pe(features, self.feape) if refine else \
+                features.new_zeros(features.shape[0], self.in_mlpC - features.shape[-1])
+            x = torch.cat([features, extra], dim=-1)
+        v = viewdirs if self.viewpe == 0 else torch.cat([viewdirs, self._pe(viewdirs, self.viewpe)], -1)
+        return torch.sigmoid(self.mlp_view(torch.cat([self.mlp(x), v], dim=-1)))
+
+
+class TensorBase(torch.nn.Module):
+    """models/tensorBase.py:231-636."""
+
+    def __init__(self, device, aabb, gridSize, density_n_comp=8, appearance_n_comp=24, app_dim=27,
+                 shadingMode="MLP_PE", alphaMask=None, near_far=[2.0, 6.0], density_shift=-10,
+                 alphaMask_thres=0.001, distance_scale=25, rayMarch_weight_thres=0.001, pos_pe=6,
+                 view_pe=6, fea_pe=6, featureC=128, step_ratio=2.0, fea2denseAct="softplus"):
+        super().__init__()
+        self.density_n_comp = list(density_n_comp)
+        self.app_n_comp = list(appearance_n_comp)
+        self.app_dim = app_dim
+        self.aabb = torch.nn.Parameter(aabb, requires_grad=False)
+        self.alphaMask = alphaMask
+        self.device = device
+        self.density_shift = density_shift
+        self.alphaMask_thres = alphaMask_thres
+        self.distance_scale = distance_scale
+        self.rayMarch_weight_thres = rayMarch_weight_thres
+        self.fea2denseAct = fea2denseAct
+        self.near_far = list(near_far)
+        self.step_ratio = step_ratio
+        self.matMode = [list(m) for m in MAT_MODE]
+        self.vecMode = list(VEC_MODE)
+        self.comp_w = [1, 1, 1]
+        self.update_stepSize(list(gridSize))
+        self.init_svd_volume(gridSize, device)
+        self.shadingMode, self.pos_pe, self.view_pe, self.fea_pe, self.featureC = (
+            shadingMode, pos_pe, view_pe, fea_pe, featureC)
+        self.init_render_func(shadingMode, pos_pe, view_pe, fea_pe, featureC, device)
+        self._prepared = None
+        self.last_weights = None     # set by forward(..., return_weights=True)
+
+    # -- construction helpers ---------------------------------------------------------------------
+    def init_render_func(self, shadingMode, pos_pe, view_pe, fea_pe, featureC, device):
+        # Only "MLP_Fea_late_view" accepts the 4-argument renderModule call of
+        # TensorBase.forward (tensorBase.py:627-629); the other modes are dead options there.
+        if shadingMode != "MLP_Fea_late_view":
+            raise NotImplementedError(
+                f"shadingMode={shadingMode!r}: only 'MLP_Fea_late_view' is usable on the "
+                "reference's render path (tensorBase.py:627-629) and built here")
+        self.renderModule = MLPRender_Fea_late_view(self.app_dim, view_pe, fea_pe, featureC).to(device)
+
+    def update_stepSize(self, gridSize):
+        """tensorBase.py:317-328 -- derives stepSize / nSamples from the grid resolution."""
+        self.aabbSize = self.aabb[1] - self.aabb[0]
+        self.invaabbSize = torch.nn.Parameter(2.0 / self.aabbSize, requires_grad=False)
+        self.gridSize = torch.LongTensor(list(gridSize)).to(self.device)
+        self._grid_host = [int(g) for g in gridSize]
+        self.units = self.aabbSize / (self.gridSize - 1)
+        self.stepSize = torch.mean(self.units) * self.step_ratio
+        self.aabbDiag = torch.sqrt(torch.sum(torch.square(self.aabbSize)))
+        self.nSamples = int((self.aabbDiag / self.stepSize).item()) + 1
+
+    def init_svd_volume(self, res, device):
+        raise NotImplementedError
+
+    def normalize_coord(self, xyz_sampled):
+        return (xyz_sampled - self.aabb[0]) * self.invaabbSize - 1
+
+    def get_kwargs(self):
+        return {
+            "aabb": self.aabb, "gridSize": self.gridSize.tolist(),
+            "density_n_comp": self.density_n_comp, "appearance_n_comp": self.app_n_comp,
+            "app_dim": self.app_dim, "density_shift": self.density_shift,
+            "alphaMask_thres": self.alphaMask_thres, "distance_scale": self.distance_scale,
+            "rayMarch_weight_thres": self.rayMarch_weight_thres, "fea2denseAct": self.fea2denseAct,
+            "near_far": self.near_far, "step_ratio": self.step_ratio,
+            "shadingMode": self.shadingMode, "pos_pe": self.pos_pe, "view_pe": self.view_pe,
+            "fea_pe": self.fea_pe, "featureC": self.featureC,
+        }
+
+    def to(self, device):
+        self.device = torch.device(device)
+        self.stepSize = self.stepSize.to(device)
+        if self.alphaMask is not None:
+            self.alphaMask = self.alphaMask.to(device)
+        self._prepared = None
+        return super().to(device)
+
+    # -- the per-batch distance table (tensorBase.py:419-437) -------------------------------------
+    def sample_table(self, is_train=False, N_samples=-1, device=None):
+        """z_vals of sample_ray_contracted: identical for every ray of the batch ([S] tensor).
+
+        Train mode draws the two jitter tensors with torch.rand_like in the reference's order so a
+        seeded run consumes the RNG stream exactly like the reference does.
+        """
+        device = device if device is not None else self.aabb.device
+        n = (N_samples if N_samples > 0 else self.nSamples) // 6
+        if not is_train:   # deterministic: build once per (n, device)
+            key = (n, str(device))
+            cached = self.__dict__.get("_ztab")
+            if cached is None or cached[0] != key:
+                cached = (key, self._build_table(n, device, False))
+                self.__dict__["_ztab"] = cached
+            return cached[1]
+        return self._build_table(n, device, True)
+
+    @staticmethod
+    def _build_table(n, device, is_train):
+        t = torch.linspace(0.0, n - 1, n, device=device)[None] / n
+        near_t = t.clone()
+        if is_train:
+            near_t += torch.rand_like(t) / n
+            t += torch.rand_like(t) / n
+        far_t = 1.0 / (1.0 * (1.0 - t) + 1.0 / 1e3 * t)
+        z = torch.cat([near_t, far_t], dim=1)
+        z += 1e-1
+        return z.reshape(-1).contiguous()
+
+    def feature2density(self, density_features):
+        if self.fea2denseAct == "softplus":
+            return F.softplus(density_features + self.density_shift)
+        if self.fea2denseAct == "relu":
+            return F.relu(density_features)
+        raise ValueError(self.fea2denseAct)
+
+    # -- C-ABI marshalling ------------------------------------------------------------------------
+    def _field_struct(self, z=None, need_mlp=True):
+        s = _lib.LrfField()
+        keep = []
+        g = self._grid_host
+        aabb = self._host_copy("_aabb_host", self.aabb)
+        for i in range(3):
+            s.grid[i] = int(g[i])
+        for i in range(6):
+            s.aabb[i] = aabb[i]
+        if len(set(self.density_n_comp)) != 1 or len(set(self.app_n_comp)) != 1:
+            raise NotImplementedError("per-plane component counts must be equal")
+        s.n_dcomp, s.n_acomp = self.density_n_comp[0], self.app_n_comp[0]
+        for i in range(3):
+            for name, plist in (("dplane", self.density_plane), ("dline", self.density_line),
+                                ("aplane", self.app_plane), ("aline", self.app_line)):
+                p = plist[i]
+                _require_cuda(p, f"{name}[{i}]")
+                t = p.detach()
+                if t.dtype != torch.float32:
+                    raise TypeError(f"{name}[{i}] must be float32, got {t.dtype}")
+                if not t.is_contiguous(memory_format=torch.channels_last):
+                    t = _cl(t)      # e.g. a parameter swapped in from outside in NCHW layout
+                    keep.append(t)
+                getattr(s, name)[i] = t.data_ptr()
+        s.app_dim = self.app_dim
+        s.featureC = self.featureC
+        s.fea_pe, s.view_pe = self.fea_pe, self.view_pe
+        if need_mlp:
+            rm = self.renderModule
+            for name, t in (("basis", self.basis_mat.weight), ("w1", rm.mlp[0].weight),
+                            ("b1", rm.mlp[0].bias), ("w2", rm.mlp[2].weight),
+                            ("b2", rm.mlp[2].bias), ("w3", rm.mlp_view[0].weight),
+                            ("b3", rm.mlp_view[0].bias)):
+                _require_cuda(t, name)
+                t = t.detach()
+                if not t.is_contiguous():
+                    t = t.contiguous(); keep.append(t)
+                setattr(s, name, t.data_ptr())
+        else:
+            s.basis = self.basis_mat.weight.detach().data_ptr()
+        if self.alphaMask is not None:
+            vol = self.alphaMask.alpha_volume.detach()
+            _require_cuda(vol, "alphaMask.alpha_volume")
+            vol = vol.contiguous()
+            keep.append(vol)
+            s.alpha_vol = vol.data_ptr()
+            for i in range(3):
+                s.alpha_dims[i] = vol.shape[-3 + i]
+            ab = self._host_copy("_alpha_aabb_host", self.alphaMask.aabb)
+            for i in range(6):
+                s.alpha_aabb[i] = ab[i]
+        s.density_shift = float(self.density_shift)
+        s.distance_scale = float(self.distance_scale)
+        s.weight_thres = float(self.rayMarch_weight_thres)
+        s.act = {"softplus": 0, "relu": 1}[self.fea2denseAct]
+        if z is not None:
+            s.z_vals = z.data_ptr()
+            s.n_samples = z.numel()
+        return s, keep
+
+    def _host_copy(self, slot, param):
+        """Host mirror of a small device tensor, refreshed only when the tensor object or its
+        version counter changes (load_state_dict / in-place edits) -- keeps the per-call path free
+        of device->host synchronisation."""
+        key = (id(param), param._version, param.device)
+        cached = self.__dict__.get(slot)
+        if cached is None or cached[0] != key:
+            cached = (key, param.detach().reshape(-1).tolist())
+            self.__dict__[slot] = cached
+        return cached[1]
+
+    def prepare(self, field_struct):
+        """(Re)builds the folded / re-laid-out MLP block the kernel stages into shared memory."""
+        dev = self.basis_mat.weight.device
+        if self._prepared is None or self._prepared.device != dev:
+            n = _lib.lib().lrf_prepared_bytes() // 4
+            self._prepared = torch.empty(n, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().lrf_field_prepare(C.byref(field_struct), _ptr(self._prepared),
+                                                _stream(dev)))
+        return self._prepared
+
+    def _check_no_autograd(self, *tensors):
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+            raise NotImplementedError(
+                "localrf_b200: the fused backward is not built yet (SURVEY.md §8f rank 1); call "
+                "the render path under torch.no_grad()")
+
+    # -- the hot path ------------------------------------------------------------------------------
+    def forward(self, rays_chunk, white_bg=True, is_train=False, N_samples=-1, refine=True,
+                floater_thresh=0, return_weights=False, stats=None, z_vals=None):
+        """tensorBase.py:567-636 -> (rgb_map [N,3], depth_map [N]).
+
+        `return_weights=True` additionally stores the final per-sample weights [N,S] in
+        `self.last_weights` (the default return arity is the reference's).  `z_vals` overrides the
+        distance table (parity tests feed the reference's own jittered table).
+        """
+        _require_cuda(rays_chunk, "rays_chunk")
+        self._check_no_autograd(rays_chunk, *self.parameters())
+        dev = rays_chunk.device
+        rays = rays_chunk.detach()
+        if rays.dtype != torch.float32 or rays.dim() != 2 or rays.shape[1] < 6:
+            raise ValueError("rays_chunk must be a float32 [N, 6] tensor")
+        rays = rays[:, :6].contiguous()
+        n = rays.shape[0]
+        if z_vals is None:
+            z = self.sample_table(is_train, N_samples, dev)
+        else:
+            z = z_vals.detach().to(dev, torch.float32).reshape(-1).contiguous()
+        # tensorBase.py:633 -- the coin is only tossed when white_bg is False and is_train
+        bg = bool(white_bg) or bool(is_train and torch.rand((1,)) < 0.5)
+        with torch.cuda.device(dev):
+            fs, keep = self._field_struct(z)
+            prep = self.prepare(fs)
+            rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
+            depth = torch.empty(n, dtype=torch.float32, device=dev)
+            weights = torch.empty(n, z.numel(), dtype=torch.float32, device=dev) if return_weights else None
+            b = _lib.LrfBatch()
+            b.n_rays = n
+            b.rays = rays.data_ptr()
+            b.n_views = 1
+            b.white_bg = int(bg)
+            b.floater_thresh = float(floater_thresh)
+            o = _lib.LrfOutputs()
+            o.rgb, o.depth = rgb.data_ptr(), depth.data_ptr()
+            if weights is not None:
+                o.weights = weights.data_ptr()
+            if stats is not None:
+                o.stats = stats.data_ptr()
+            _lib.check(_lib.lib().lrf_render(C.byref(fs), _ptr(prep), C.byref(b), C.byref(o),
+                                             _stream(dev)))
+        self.last_weights = weights
+        return rgb, depth
+
+    # -- off-path methods of the reference (host bookkeeping, stock torch) ------------------------
+    def compute_alpha(self, xyz_locs, length=1):
+        """tensorBase.py:538-558."""
+        if self.alphaMask is not None:
+            keep = self.alphaMask.sample_alpha(xyz_locs) > 0
+        else:
+            keep = torch.ones_like(xyz_locs[:, 0], dtype=torch.bool)
+        sigma = torch.zeros(xyz_locs.shape[:-1], device=xyz_locs.device)
+        if keep.any():
+            feat = self.compute_densityfeature(self.normalize_coord(xyz_locs[keep]))
+            sigma[keep] = self.feature2density(feat)
+        return 1 - torch.exp(-sigma * length).view(xyz_locs.shape[:-1])
+
+    @torch.no_grad()
+    def getDenseAlpha(self, gridSize=None):
+        """tensorBase.py:501-515 -- alpha on a dense lattice of the aabb, slab by slab."""
+        gridSize = self.gridSize if gridSize is None else gridSize
+        dev = self.aabb.device
+        axes = [torch.linspace(0, 1, int(n), device=dev) for n in gridSize]
+        lattice = torch.stack(torch.meshgrid(*axes, indexing="ij"), -1)
+        lattice = self.aabb[0] * (1 - lattice) + self.aabb[1] * lattice
+        alpha = torch.zeros_like(lattice[..., 0])
+        for i in range(int(gridSize[0])):
+            alpha[i] = self.compute_alpha(lattice[i].view(-1, 3), self.stepSize).view(
+                int(gridSize[1]), int(gridSize[2]))
+        return alpha
+
+    @torch.no_grad()
+    def updateAlphaMask(self, gridSize=(200, 200, 200)):
+        """tensorBase.py:517-536 -- rebuilt ON THE DEVICE (the reference moves the model to the CPU)."""
+        gridSize = tuple(int(g) for g in gridSize)
+        alpha = self.getDenseAlpha(gridSize).clamp(0, 1).transpose(0, 2).contiguous()[None, None]
+        alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1).view(gridSize[::-1])
+        alpha = (alpha >= self.alphaMask_thres).to(alpha.dtype)
+        self.alphaMask = AlphaGridMask(self.aabb.device, self.aabb.detach(), alpha)
+        kept = float(alpha.sum()) / (gridSize[0] * gridSize[1] * gridSize[2]) * 100
+        print(f"alpha rest %%%f" % kept)
+
+
+class TensorVMSplit(TensorBase):
+    """models/tensoRF.py:10-277 -- vector-matrix decomposed density / appearance grids."""
+
+    def __init__(self, device, aabb, gridSize, **kargs):
+        super().__init__(device, aabb, gridSize, **kargs)
+
+    def init_svd_volume(self, res, device):
+        self.density_plane, self.density_line = self.init_one_svd(self.density_n_comp, res, 0.1, device)
+        self.app_plane, self.app_line = self.init_one_svd(self.app_n_comp, res, 0.1, device)
+        self.basis_mat = torch.nn.Linear(sum(self.app_n_comp), self.app_dim, bias=False).to(device)
+
+    def init_one_svd(self, n_component, gridSize, scale, device):
+        """tensoRF.py:29-50; same shapes and init draws, channels_last storage."""
+        planes, lines = [], []
+        for i, (vec_id, (m0, m1)) in enumerate(zip(self.vecMode, self.matMode)):
+            # the reference draws plane then line for each i, on the CPU generator
+            p = scale * torch.randn((1, n_component[i], gridSize[m1], gridSize[m0]))
+            l = scale * torch.randn((1, n_component[i], gridSize[vec_id], 1))
+            planes.append(torch.nn.Parameter(_cl(p.to(device))))
+            lines.append(torch.nn.Parameter(_cl(l.to(device))))
+        return torch.nn.ParameterList(planes), torch.nn.ParameterList(lines)
+
+    def get_optparam_groups(self, lr_init_spatialxyz=0.02, lr_init_network=0.001):
+        groups = [{"params": p, "lr": lr_init_spatialxyz}
+                  for p in (self.density_line, self.density_plane, self.app_line, self.app_plane)]
+        groups.append({"params": self.basis_mat.parameters(), "lr": lr_init_network})
+        if isinstance(self.renderModule, torch.nn.Module):
+            groups.append({"params": self.renderModule.parameters(), "lr": lr_init_network})
+        return groups
+
+    # -- feature lookups through the C ABI ---------------------------------------------------------
+    def _feature_call(self, xyz_sampled, fn_name, width):
+        _require_cuda(xyz_sampled, "xyz_sampled")
+        self._check_no_autograd(xyz_sampled, *self.density_plane, *self.app_plane)
+        dev = xyz_sampled.device
+        xyz = xyz_sampled.detach().reshape(-1, 3).to(torch.float32).contiguous()
+        m = xyz.shape[0]
+        out = torch.empty((m,) if width == 1 else (m, width), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            fs, keep = self._field_struct(None, need_mlp=False)
+            fn = getattr(_lib.lib(), fn_name)
+            _lib.check(fn(C.byref(fs), _ptr(xyz), m, _ptr(out), _stream(dev)))
+        return out
+
+    def compute_densityfeature(self, xyz_sampled):
+        """tensoRF.py:112-151: [M,3] normalised coords -> [M]."""
+        return self._feature_call(xyz_sampled, "lrf_density_feature", 1)
+
+    def compute_appfeature(self, xyz_sampled):
+        """tensoRF.py:153-196: [M,3] normalised coords -> [M, app_dim]."""
+        return self._feature_call(xyz_sampled, "lrf_app_feature", self.app_dim)
+
+    # -- regularisers (tensoRF.py:66-110), stock torch ---------------------------------------------
+    def vectorDiffs(self, vector_comps):
+        total = 0
+        for v in vector_comps:
+            n_comp, n_size = v.shape[1:-1]
+            m = v.reshape(n_comp, n_size)
+            gram = m @ m.t()
+            off_diag = gram.reshape(-1)[1:].view(n_comp - 1, n_comp + 1)[..., :-1]
+            total = total + off_diag.abs().mean()
+        return total
+
+    def vector_comp_diffs(self):
+        return self.vectorDiffs(self.density_line) + self.vectorDiffs(self.app_line)
+
+    def density_L1(self):
+        g = self.gridSize
+        n_vox = int(torch.prod(g))
+        feat = torch.zeros(n_vox, device=g.device)
+        for i in range(3):
+            plane = self.density_plane[i].reshape(-1, int(torch.prod(g[self.matMode[i]])))
+            line = self.density_line[i].reshape(-1, int(g[self.vecMode[i]]))
+            feat = feat + torch.bmm(plane[..., None], line[:, None]).view(-1, n_vox).sum(0)
+        return torch.sqrt(self.feature2density(feat).clamp(1e-5)).mean()
+
+    def _tv(self, planes, lines, reg):
+        total = 0
+        for p, l in zip(planes, lines):
+            total = total + reg(p.transpose(0, 1)) * 1e-2 + reg(l.transpose(0, 1)) * 1e-3
+        return total
+
+    def TV_loss_density(self, reg):
+        return self._tv(self.density_plane, self.density_line, reg)
+
+    def TV_loss_app(self, reg):
+        return self._tv(self.app_plane, self.app_line, reg)
+
+    # -- resolution schedule (tensoRF.py:198-233) --------------------------------------------------
+    @torch.no_grad()
+    def up_sampling_VM(self, plane_coef, line_coef, res_target):
+        for i, (vec_id, (m0, m1)) in enumerate(zip(self.vecMode, self.matMode)):
+            p = F.interpolate(plane_coef[i].detach(), size=(res_target[m1], res_target[m0]),
+                              mode="bilinear", align_corners=True)
+            l = F.interpolate(line_coef[i].detach(), size=(res_target[vec_id], 1),
+                              mode="bilinear", align_corners=True)
+            plane_coef[i] = torch.nn.Parameter(_cl(p))
+            line_coef[i] = torch.nn.Parameter(_cl(l))
+        return plane_coef, line_coef
+
+    @torch.no_grad()
+    def upsample_volume_grid(self, res_target):
+        self.app_plane, self.app_line = self.up_sampling_VM(self.app_plane, self.app_line, res_target)
+        self.density_plane, self.density_line = self.up_sampling_VM(
+            self.density_plane, self.density_line, res_target)
+        self.update_stepSize(res_target)
+        print(f"upsamping to {res_target}")

@@ -1,0 +1,51 @@
+"""CPU-only: the C-ABI library builds, loads and exports every symbol include/localrf_b200.h declares
+(no compute calls without a GPU), and argument validation works without touching a device."""
+import ctypes as C
+import os
+import re
+
+from localrf_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "localrf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lrf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    L = _lib.lib()
+    syms = declared_symbols()
+    assert "lrf_render" in syms and "lrf_field_prepare" in syms
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in the header but not exported"
+    assert sorted(_lib.EXPORTS) == syms
+
+
+def test_version_and_prepared_size():
+    L = _lib.lib()
+    assert L.lrf_version() == 1
+    # W1B[72][128] + W2T[128][128] + b1 + b2 + W3[3][132] + b3[4] floats
+    assert L.lrf_prepared_bytes() == 4 * (72 * 128 + 128 * 128 + 128 + 128 + 3 * 132 + 4)
+
+
+def test_struct_sizes_match_c_layout():
+    # natural-alignment layouts of the header structs (x86-64)
+    assert C.sizeof(_lib.LrfOutputs) == 5 * 8
+    assert C.sizeof(_lib.LrfBatch) == 120
+    assert C.sizeof(_lib.LrfField) % 8 == 0
+
+
+def test_validation_errors_without_gpu():
+    L = _lib.lib()
+    f = _lib.LrfField()
+    f.n_dcomp, f.n_acomp = 16, 24        # unsupported component count
+    rc = L.lrf_density_feature(C.byref(f), None, 0, None, None)
+    assert rc == -2 and b"density_n_comp" in L.lrf_last_error()
+    f.n_dcomp = 8
+    rc = L.lrf_density_feature(C.byref(f), None, 0, None, None)
+    assert rc == -1                       # gridSize 0
+    rc = L.lrf_render(C.byref(f), None, None, None, None)
+    assert rc == -1

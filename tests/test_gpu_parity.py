@@ -1,0 +1,129 @@
+"""-m gpu: the CUDA path (through the Python mirror and the raw C ABI) against the golden vectors
+of the unmodified reference and against the pinned CPU oracle.  Tolerance: 1e-4 relative, fp32
+(BASELINE.json north_star); see test_oracle_golden.py for why per-sample weights sit at the bound."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import full_field_dict, load_golden, rel_err
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def cfg1():
+    from gpu_helpers import module_from_golden
+    g = load_golden("cfg1_64")
+    return g, module_from_golden(g)
+
+
+def _run(m, g, case, **kw):
+    rays = torch.from_numpy(g["rays"]).cuda()
+    z = torch.from_numpy(g[f"{case}.z"]).cuda()
+    with torch.no_grad():
+        rgb, depth = m(rays, return_weights=True, z_vals=z, **kw)
+    torch.cuda.synchronize()
+    return rgb.cpu().numpy(), depth.cpu().numpy(), m.last_weights.cpu().numpy()
+
+
+@pytest.mark.parametrize("case,kw", [
+    ("eval", dict()),
+    ("eval_floater", dict(floater_thresh=0.5)),
+    ("eval_nobg", dict(white_bg=False)),
+    ("train", dict(is_train=True)),
+])
+def test_cfg1_vs_reference_golden(cfg1, case, kw):
+    g, m = cfg1
+    rgb, depth, w = _run(m, g, case, **kw)
+    assert rel_err(rgb, g[f"{case}.rgb"]) < TOL
+    assert rel_err(depth, g[f"{case}.depth"]) < TOL
+    assert rel_err(w, g[f"{case}.weights"], floor=1e-3) < TOL
+
+
+def test_cfg1_eval_table_matches(cfg1):
+    g, m = cfg1
+    z = m.sample_table(False, -1, torch.device("cuda")).cpu().numpy()
+    np.testing.assert_allclose(z, g["eval.z"], rtol=1e-7, atol=0)
+
+
+def test_feature_entry_points(cfg1):
+    g, m = cfg1
+    xyz = torch.from_numpy(g["unit.xyz"]).cuda()
+    with torch.no_grad():
+        d = m.compute_densityfeature(xyz).cpu().numpy()
+        a = m.compute_appfeature(xyz).cpu().numpy()
+    assert rel_err(d, g["unit.density_feature"], floor=1e-2) < TOL
+    assert rel_err(a, g["unit.app_feature"], floor=1e-2) < TOL
+
+
+@pytest.mark.parametrize("name,cases", [
+    ("opaque_32", [("eval", {}), ("eval_floater", dict(floater_thresh=0.5))]),
+    ("relu_32", [("eval", {})]),
+    ("alphamask_32", [("eval", {})]),
+])
+def test_small_fields_vs_reference_golden(name, cases):
+    from gpu_helpers import module_from_golden
+    g = load_golden(name)
+    m = module_from_golden(g)
+    for case, kw in cases:
+        rgb, depth, w = _run(m, g, case, **kw)
+        assert rel_err(rgb, g[f"{case}.rgb"]) < TOL, (name, case)
+        assert rel_err(depth, g[f"{case}.depth"]) < TOL, (name, case)
+        assert rel_err(w, g[f"{case}.weights"], floor=1e-3) < TOL, (name, case)
+
+
+def test_positional_encoding_is_reported_unsupported():
+    from gpu_helpers import module_from_golden
+    g = load_golden("aniso_pe")
+    m = module_from_golden(g)
+    with pytest.raises(NotImplementedError):
+        with torch.no_grad():
+            m(torch.from_numpy(g["rays"]).cuda())
+
+
+def test_anisotropic_grid_vs_oracle():
+    """Axis mix-ups show on a [40,52,64] grid; checker = the pinned oracle on seeded inputs."""
+    import localrf_b200 as L
+    from gpu_helpers import AABB, field_kwargs
+    torch.manual_seed(31)
+    sc = dict(app_dim=27, density_shift=-5.0, distance_scale=25.0, rayMarch_weight_thres=1e-3,
+              view_pe=0, fea_pe=0, featureC=128, step_ratio=0.5, fea2denseAct="softplus")
+    m = L.TensorVMSplit("cuda", AABB.clone().cuda(), [40, 52, 64], **field_kwargs(sc))
+    fd = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    fd.update(sc); fd["gridSize"] = [40, 52, 64]
+    f = orc.Field(fd)
+    gen = torch.Generator().manual_seed(32)
+    rays = torch.cat([0.3 * torch.randn(300, 3, generator=gen), torch.randn(300, 3, generator=gen)], -1)
+    z = orc.sample_table(f.n_samples())
+    assert m.nSamples == f.n_samples()
+    for thr in (0.0, 0.5):
+        ref = orc.field_forward(f, rays.numpy(), z, floater_thresh=thr)
+        with torch.no_grad():
+            rgb, depth = m(rays.cuda(), floater_thresh=thr, return_weights=True)
+        assert rel_err(rgb.cpu().numpy(), ref["rgb"]) < TOL
+        assert rel_err(depth.cpu().numpy(), ref["depth"]) < TOL
+        assert rel_err(m.last_weights.cpu().numpy(), ref["weights"], floor=1e-3) < TOL
+
+
+def test_ragged_and_empty_batches(cfg1):
+    g, m = cfg1
+    rays = torch.from_numpy(g["rays"]).cuda()
+    with torch.no_grad():
+        full_rgb, full_depth = m(rays)
+        for n in (0, 1, 7, 9, 511):
+            rgb, depth = m(rays[:n])
+            assert rgb.shape == (n, 3) and depth.shape == (n,)
+            assert torch.equal(rgb, full_rgb[:n]) and torch.equal(depth, full_depth[:n])
+
+
+def test_ray_order_invariance_bit_exact(cfg1):
+    """Per-ray results do not depend on which tile / CTA a ray lands in."""
+    g, m = cfg1
+    rays = torch.from_numpy(g["rays"]).cuda()
+    perm = torch.randperm(rays.shape[0], generator=torch.Generator().manual_seed(5)).cuda()
+    with torch.no_grad():
+        rgb, depth = m(rays)
+        rgb_p, depth_p = m(rays[perm])
+    assert torch.equal(rgb[perm], rgb_p) and torch.equal(depth[perm], depth_p)
