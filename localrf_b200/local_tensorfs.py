@@ -268,7 +268,9 @@ class LocalTensorfs(torch.nn.Module):
             if re.fullmatch(r"tensorfs.[1-9][0-9]*.density_plane.0", key):
                 plane0 = state_dict[key]
                 line0 = state_dict[key[: -len("density_plane.0")] + "density_line.0"]
-                self.tensorf_args["gridSize"] = [plane0.shape[2], plane0.shape[3], line0.shape[2]]
+                # plane 0 is [1,C,G_y,G_x], line 0 is [1,C,G_z,1].  (The reference reads x and y
+                # swapped here, which only works for G_x == G_y; the intended order is used.)
+                self.tensorf_args["gridSize"] = [plane0.shape[3], plane0.shape[2], line0.shape[2]]
                 self.append_rf()
         for i, rf in enumerate(self.tensorfs):
             if f"tensorfs.{i}.alphaMask.aabb" in state_dict:

@@ -36,7 +36,7 @@ def module_from_golden(g, device="cuda"):
 def local_from_golden(g, device="cuda"):
     sc = field_scalars(g)
     kw = field_kwargs(sc)
-    lt = L.LocalTensorfs(camera_prior=None, fov=float(g["fov"]), n_init_frames=1, n_overlap=30,
+    lt = L.LocalTensorfs(camera_prior=None, fov=float(g["fov"]), n_init_frames=4, n_overlap=30,
                          WH=tuple(int(v) for v in g["WH"]), n_iters_per_frame=600, n_iters_reg=100,
                          lr_R_init=5e-3, lr_t_init=5e-4, lr_i_init=0, lr_exposure_init=1e-3,
                          rf_lr_init=2e-2, rf_lr_basis=1e-3, lr_decay_target_ratio=0.1,
