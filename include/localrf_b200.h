@@ -125,6 +125,12 @@ int lrf_field_prepare(const LrfField *field, void *prepared, lrf_stream_t stream
 int lrf_render(const LrfField *field, const void *prepared, const LrfBatch *batch,
                const LrfOutputs *out, lrf_stream_t stream);
 
+/* basis_mat + MLPRender_Fea_late_view.forward (tensoRF.py:196 + tensorBase.py:115-135, pe = 0) on
+ * explicit inputs: feats [M][72] = the plane x line products (tensoRF.py:192-194 order: plane-major,
+ * channel-minor), viewdirs [M][3] normalised -> rgb [M][3].  Same tensor-core code as lrf_render. */
+int lrf_mlp_forward(const void *prepared, const float *feats, const float *viewdirs, int64_t M,
+                    float *rgb, lrf_stream_t stream);
+
 /* compute_densityfeature (tensoRF.py:112-151): xyz_norm [M][3] in [-1,1]^3 -> out [M] */
 int lrf_density_feature(const LrfField *field, const float *xyz_norm, int64_t M, float *out,
                         lrf_stream_t stream);

@@ -65,7 +65,7 @@ class LrfOutputs(C.Structure):
 
 
 EXPORTS = ["lrf_version", "lrf_last_error", "lrf_prepared_bytes", "lrf_field_prepare",
-           "lrf_render", "lrf_density_feature", "lrf_app_feature", "lrf_repack_nchw_to_nhwc",
+           "lrf_render", "lrf_mlp_forward", "lrf_density_feature", "lrf_app_feature", "lrf_repack_nchw_to_nhwc",
            "lrf_launch_info"]
 
 
@@ -114,6 +114,7 @@ def lib():
     L.lrf_prepared_bytes.restype = C.c_size_t
     L.lrf_field_prepare.argtypes = [C.POINTER(LrfField), _vp, _vp]
     L.lrf_render.argtypes = [C.POINTER(LrfField), _vp, C.POINTER(LrfBatch), C.POINTER(LrfOutputs), _vp]
+    L.lrf_mlp_forward.argtypes = [_vp, _vp, _vp, C.c_int64, _vp, _vp]
     L.lrf_density_feature.argtypes = [C.POINTER(LrfField), _vp, C.c_int64, _vp, _vp]
     L.lrf_app_feature.argtypes = [C.POINTER(LrfField), _vp, C.c_int64, _vp, _vp]
     L.lrf_repack_nchw_to_nhwc.argtypes = [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]

@@ -12,8 +12,10 @@ size_t render_smem_bytes(int S, bool floater);
 int render_threads();
 cudaError_t launch_render(const FieldDev& F, const BatchDev& B, int n_sms, cudaStream_t stream);
 cudaError_t launch_prepare(const float* basis, const float* w1, const float* b1, const float* w2,
-                           const float* b2, const float* w3, const float* b3, float* prep,
+                           const float* b2, const float* w3, const float* b3, unsigned char* prep,
                            cudaStream_t stream);
+cudaError_t launch_mlp(const float* prep, const float* feats, const float* viewdirs, long long M,
+                       float* rgb, int n_sms, cudaStream_t stream);
 cudaError_t launch_density_feature(const FieldDev& F, const float* xyz, long long M, float* out,
                                    cudaStream_t stream);
 cudaError_t launch_app_feature(const FieldDev& F, const float* basis, const float* xyz,
@@ -122,7 +124,7 @@ int lrf_version(void) { return 1; }
 
 const char* lrf_last_error(void) { return g_err; }
 
-size_t lrf_prepared_bytes(void) { return (size_t)lrf::PREP_FLOATS * sizeof(float); }
+size_t lrf_prepared_bytes(void) { return (size_t)lrf::PREP_BYTES; }
 
 int lrf_field_prepare(const LrfField* f, void* prepared, lrf_stream_t stream) {
   if (!f || !prepared) return fail(LRF_ERR_INVALID, "field or prepared is NULL");
@@ -134,7 +136,7 @@ int lrf_field_prepare(const LrfField* f, void* prepared, lrf_stream_t stream) {
   if (!f->basis || !f->w1 || !f->b1 || !f->w2 || !f->b2 || !f->w3 || !f->b3)
     return fail(LRF_ERR_INVALID, "MLP / basis pointer is NULL");
   cudaError_t e = lrf::launch_prepare(f->basis, f->w1, f->b1, f->w2, f->b2, f->w3, f->b3,
-                                      static_cast<float*>(prepared), (cudaStream_t)stream);
+                                      static_cast<unsigned char*>(prepared), (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "prepare_kernel");
   return LRF_OK;
 }
@@ -188,6 +190,19 @@ int lrf_render(const LrfField* f, const void* prepared, const LrfBatch* b, const
     return fail(LRF_ERR_UNSUPPORTED, "sample table too long for the shared-memory budget");
   cudaError_t e = lrf::launch_render(F, B, d.n_sms, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "render_kernel");
+  return LRF_OK;
+}
+
+int lrf_mlp_forward(const void* prepared, const float* feats, const float* viewdirs, int64_t M,
+                    float* rgb, lrf_stream_t stream) {
+  if (!prepared) return fail(LRF_ERR_INVALID, "prepared is NULL (call lrf_field_prepare first)");
+  if (M < 0 || (M > 0 && (!feats || !viewdirs || !rgb))) return fail(LRF_ERR_INVALID, "bad feats/viewdirs/rgb/M");
+  DevInfo d;
+  int rc = device_info(d);
+  if (rc != LRF_OK) return rc;
+  cudaError_t e = lrf::launch_mlp(static_cast<const float*>(prepared), feats, viewdirs, M, rgb,
+                                  d.n_sms, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "mlp_kernel");
   return LRF_OK;
 }
 

@@ -16,20 +16,32 @@ __host__ __device__ constexpr int mat0(int i) { return i == 2 ? 1 : 0; }
 __host__ __device__ constexpr int mat1(int i) { return i == 0 ? 1 : 2; }
 __host__ __device__ constexpr int vecm(int i) { return 2 - i; }
 
-// Layout of the per-field prepared block (floats).  All matrices are k-major ("transposed") so a
-// thread block reads rows of consecutive outputs.
-//   W1B [NF][FC]  : (mlp[0].weight @ basis_mat.weight)^T  -- basis (72->27) folded into layer 1
-//   W2T [FC][FC]  : mlp[2].weight^T
-//   B1 [FC], B2 [FC], W3 [3][FC+3] (row-major, padded to 3*132), B3 [4]
-constexpr int PREP_W1B = 0;
-constexpr int PREP_W2T = PREP_W1B + NF * FC;
-constexpr int PREP_B1 = PREP_W2T + FC * FC;
-constexpr int PREP_B2 = PREP_B1 + FC;
-constexpr int PREP_W3 = PREP_B2 + FC;         // 3 rows of 132 floats (131 used)
+// Layout of the per-field prepared block (BYTES).  The two dense layers are stored as bf16 hi/lo
+// pairs (w = hi + lo to ~16 mantissa bits) already in the shared-memory image the tensor core reads:
+// K-major, no swizzle, 8x8 core matrices ([row group][k chunk][8 rows][8 bf16 = 16 B]).
+//   B1 : W1B[n][k] = (mlp[0].weight @ basis_mat.weight)[n][k], n < 128, k < 72 (+8 zero pad)
+//   B2 : mlp[2].weight[n][k], n, k < 128
+// followed by the fp32 tail: b1[128], b2[128], W3[3][132] (131 used), b3[4].
+constexpr int K1 = 80;                       // layer-1 K padded to a multiple of 16
+constexpr int K1_CHUNKS = K1 / 8;            // 10 16-byte chunks per row
+constexpr int K2_CHUNKS = FC / 8;            // 16
+constexpr int OPER1_BYTES = 16 * K1_CHUNKS * 128;   // one [128 x 80] bf16 operand   = 20480
+constexpr int OPER2_BYTES = 16 * K2_CHUNKS * 128;   // one [128 x 128] bf16 operand  = 32768
+constexpr int PREP_B1HI = 0;
+constexpr int PREP_B1LO = PREP_B1HI + OPER1_BYTES;
+constexpr int PREP_B2HI = PREP_B1LO + OPER1_BYTES;
+constexpr int PREP_B2LO = PREP_B2HI + OPER2_BYTES;
+constexpr int PREP_TAIL = PREP_B2LO + OPER2_BYTES;  // fp32 from here
 constexpr int W3_LD = 132;
-constexpr int PREP_B3 = PREP_W3 + 3 * W3_LD;
-constexpr int PREP_FLOATS = PREP_B3 + 4;      // multiple of 4 -> 16-byte sized for bulk copies
-static_assert(PREP_FLOATS % 4 == 0, "prepared block must be a multiple of 16 bytes");
+constexpr int TAIL_B1 = 0, TAIL_B2 = FC, TAIL_W3 = 2 * FC, TAIL_B3 = 2 * FC + 3 * W3_LD;
+constexpr int TAIL_FLOATS = TAIL_B3 + 4;
+constexpr int PREP_BYTES = PREP_TAIL + TAIL_FLOATS * 4;
+static_assert(PREP_BYTES % 16 == 0, "prepared block must be a multiple of 16 bytes");
+
+// byte offset of element (row, k) inside a core-matrix operand image with `chunks` k-chunks per row
+__host__ __device__ constexpr int oper_offset(int row, int k, int chunks) {
+  return (((row >> 3) * chunks + (k >> 3)) * 8 + (row & 7)) * 16 + (k & 7) * 2;
+}
 
 struct FieldDev {
   int g[3];

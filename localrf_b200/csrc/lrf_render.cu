@@ -11,9 +11,16 @@
 //            ~14 voxels of path, so the warp's texel fetches fall into few 128-byte lines; the
 //            transmittance is a warp-shuffle product scan with a carried prefix.
 //   phase 2 (appearance): the tile's surviving samples are compacted (deterministically, per-ray
-//            segments) and shaded in sub-tiles of TM samples: gather 72 features per sample into
-//            shared memory, two CTA-wide GEMMs out of shared memory (weights staged once per CTA
-//            by a TMA bulk copy), layer 3 + sigmoid, weighted accumulation per ray in sample order.
+//            segments) and shaded in sub-tiles of 128 samples: gather the 72 plane x line products
+//            per sample, split them into bf16 hi/lo and store them as the K-major A operand in
+//            shared memory; layers 1 (basis folded in) and 2 run on the 5th-gen tensor cores
+//            (tcgen05.mma kind::f16, M=128 N=128, three bf16 products hi*hi + hi*lo + lo*hi per
+//            layer = ~16 mantissa bits, fp32 accumulators in TMEM); the epilogues read TMEM with
+//            tcgen05.ld, apply bias/ReLU, re-split for the next layer, and finish layer 3 +
+//            sigmoid + weighted accumulation per ray in sample order on the CUDA cores.  The
+//            weight operands are staged once per CTA by TMA bulk copies.
+#include <cuda_bf16.h>
+
 #include "lrf_common.cuh"
 
 namespace lrf {
@@ -21,7 +28,13 @@ namespace lrf {
 constexpr int THREADS = 256;
 constexpr int NWARPS = THREADS / 32;
 constexpr int RT = NWARPS;   // rays per tile
-constexpr int TM = 64;       // appearance samples per MLP sub-tile
+constexpr int TM = 128;      // appearance samples per MLP sub-tile (= UMMA M)
+constexpr int MLP_S = 192;       // pseudo sample count sizing mlp_kernel's scratch (>= TM*3*4 bytes)
+constexpr int TMEM_COLS = 256;   // acc1 [0,128) + acc2 [128,256) fp32 columns
+// tcgen05 instruction descriptor, kind::f16: D=f32 (bit4), A=B=bf16 (bits 7,10), both K-major,
+// N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FC >> 3) << 17) |
+                           ((uint32_t)(TM >> 4) << 24);
 constexpr float T_EPS = 1e-10f;  // early-termination transmittance (error bound)
 
 struct RaySm {
@@ -39,16 +52,17 @@ struct RaySm {
 
 // ---- shared-memory carve-up (dynamic) -----------------------------------------------------------
 struct SmemLayout {
-  int prep, x, h, rgb, sray, sw, w, alpha, klist, ray, z, mbar, total;
+  int prep, a, part, rgb, sray, sw, w, alpha, klist, ray, z, mbar, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(int S, bool floater) {
   SmemLayout L;
   int off = 0;
   int Sp = (S + 3) & ~3;
-  L.prep = off;  off += PREP_FLOATS * 4;
-  L.x = off;     off += NF * TM * 4;          // also reused for the layer-3 partial sums
-  L.h = off;     off += FC * TM * 4;
+  L.prep = off;  off += PREP_BYTES;               // B operands (bf16 hi/lo) + fp32 tail
+  off = (off + 1023) & ~1023;
+  L.a = off;     off += 2 * OPER2_BYTES;          // A2 hi/lo; A1 hi/lo alias its start
+  L.part = off;  off += TM * 3 * 4;               // layer-3 partial sums of the upper column half
   L.rgb = off;   off += TM * 4 * 4;
   L.sray = off;  off += TM * 4;
   L.sw = off;    off += TM * 4;
@@ -59,7 +73,7 @@ __host__ __device__ inline SmemLayout smem_layout(int S, bool floater) {
   L.ray = off;   off += RT * (int)sizeof(RaySm);
   off = (off + 15) & ~15;
   L.z = off;     off += (Sp + 4) * 4;
-  L.mbar = off;  off += 16;
+  L.mbar = off;  off += 64;                       // 3 mbarriers + the TMEM base-address slot
   L.total = off;
   return L;
 }
@@ -94,6 +108,104 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
+}
+
+// ---- PTX helpers: tcgen05 (TMEM allocation, MMA, commit, TMEM load, fences) ----------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_NONE (8x8 core matrices of 128 contiguous bytes)
+// lbo = byte stride between the two K-adjacent core matrices, sbo = between 8-row groups
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) |
+         ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread for the whole CTA
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base lane + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// x = hi + lo with hi, lo bf16 (round-to-nearest): ~16 mantissa bits.  Packs two values per word.
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  float2 hf = __bfloat1622float2(h);
+  __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+// stores 8 consecutive K elements (one 16-byte chunk) of row `row` into the hi and lo operands
+__device__ __forceinline__ void store_chunk(unsigned char* hi_base, unsigned char* lo_base, int row,
+                                            int kc, int chunks, const float* v) {
+  uint4 h, l;
+  split2(v[0], v[1], h.x, l.x);
+  split2(v[2], v[3], h.y, l.y);
+  split2(v[4], v[5], h.z, l.z);
+  split2(v[6], v[7], h.w, l.w);
+  const int off = (((row >> 3) * chunks + kc) * 8 + (row & 7)) * 16;
+  *reinterpret_cast<uint4*>(hi_base + off) = h;
+  *reinterpret_cast<uint4*>(lo_base + off) = l;
+}
+
+// One elected thread: D = Ahi*Bhi^T + Ahi*Blo^T + Alo*Bhi^T over `ksteps` K-steps of 16, then commit.
+__device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo,
+                                            uint32_t b_hi, uint32_t b_lo, int ksteps, int chunks,
+                                            uint32_t bar) {
+  const uint32_t sbo = (uint32_t)chunks * 128u;
+  uint32_t acc = 0;
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint32_t ko = (uint32_t)ks * 256u;   // two 128-byte core matrices per K-step
+    const uint64_t ah = umma_desc(a_hi + ko, 128u, sbo), al = umma_desc(a_lo + ko, 128u, sbo);
+    const uint64_t bh = umma_desc(b_hi + ko, 128u, sbo), bl = umma_desc(b_lo + ko, 128u, sbo);
+    umma_bf16(d_tmem, ah, bh, acc);
+    umma_bf16(d_tmem, ah, bl, 1u);
+    umma_bf16(d_tmem, al, bh, 1u);
+    acc = 1u;
+  }
+  umma_commit(bar);
 }
 
 // ---- ray setup (local_tensorfs.py:397-456 / tensorBase.py:578-580) ------------------------------
@@ -275,27 +387,127 @@ __device__ __forceinline__ void rescan_weights(const float* alpha_s, float* w_s,
   }
 }
 
-// ---- CTA-wide GEMM out of shared memory ---------------------------------------------------------
-// acc[i][j] = sum_k A[k][m0+i] * Wt[k][n0+j],  A: [K][TM], Wt: [K][FC];  256 threads cover TM x FC
-template <int K>
-__device__ __forceinline__ void cta_gemm(const float* __restrict__ A, const float* __restrict__ Wt,
-                                         int m0, int n0, float (&acc)[4][8]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    float4 a = *reinterpret_cast<const float4*>(A + k * TM + m0);
-    float4 w0 = *reinterpret_cast<const float4*>(Wt + k * FC + n0);
-    float4 w1 = *reinterpret_cast<const float4*>(Wt + k * FC + n0 + 4);
-    float av[4] = {a.x, a.y, a.z, a.w};
-    float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+// ---- shading of one sub-tile of TM samples whose A1 operand is already in shared memory ------------
+// layer 1 + 2 on the tensor cores, layer 3 + sigmoid on the CUDA cores.  Must be called by all
+// THREADS threads.  vd_of(m) gives the normalised view direction of sample row m (or nullptr).
+struct ShadeSmem {
+  unsigned char* prep;     // B operands + fp32 tail
+  unsigned char* a;        // A1 (aliased) / A2 operands
+  float* part;             // [TM][3]
+  float* rgb;              // [TM][4]
+  uint32_t bar1, bar2;     // mbarriers of the two MMA layers
+  uint32_t tmem;           // TMEM base address
+};
+
+template <class ViewDir>
+__device__ __forceinline__ void shade_tile(const ShadeSmem& sm, uint32_t phase, ViewDir vd_of) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* tail = reinterpret_cast<const float*>(sm.prep + PREP_TAIL);
+  const float* b1_s = tail + TAIL_B1;
+  const float* b2_s = tail + TAIL_B2;
+  const float* W3_s = tail + TAIL_W3;
+  const float* b3_s = tail + TAIL_B3;
+  const uint32_t prep_a = smem_u32(sm.prep), a_a = smem_u32(sm.a);
+  unsigned char* a2_hi = sm.a;
+  unsigned char* a2_lo = sm.a + OPER2_BYTES;
+
+  // A1 was written with generic-proxy stores: make it visible to the tensor core, then sync
+  fence_async_smem();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    issue_layer(sm.tmem, a_a, a_a + OPER1_BYTES, prep_a + PREP_B1HI, prep_a + PREP_B1LO,
+                K1 / 16, K1_CHUNKS, sm.bar1);
   }
+  mbar_wait(sm.bar1, phase);
+  tc_fence_after();
+
+  // -- epilogue 1: h1 = relu(acc1 + b1) -> bf16 hi/lo A operand of layer 2 ------------------------
+  const int q = warp & 3, half = warp >> 2;       // TMEM lane quarter, column half
+  const int row = q * 32 + lane;
+  const uint32_t t_row = sm.tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c0 = half * 64 + cc * 32;
+    float v[32];
+    tmem_ld32(t_row + (uint32_t)c0, v);
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float h[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h[e] = fmaxf(v[j + e] + b1_s[c0 + j + e], 0.0f);
+      store_chunk(a2_hi, a2_lo, row, (c0 + j) >> 3, K2_CHUNKS, h);
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    issue_layer(sm.tmem + FC, a_a, a_a + OPER2_BYTES, prep_a + PREP_B2HI, prep_a + PREP_B2LO,
+                FC / 16, K2_CHUNKS, sm.bar2);
+  }
+  mbar_wait(sm.bar2, phase);
+  tc_fence_after();
+
+  // -- epilogue 2: h2 = relu(acc2 + b2); layer 3 (131 -> 3) + sigmoid (tensorBase.py:126-133) ------
+  float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c0 = half * 64 + cc * 32;
+    float v[32];
+    tmem_ld32(t_row + (uint32_t)(FC + c0), v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float h = fmaxf(v[j] + b2_s[c0 + j], 0.0f);
+      p0 = fmaf(W3_s[0 * W3_LD + c0 + j], h, p0);
+      p1 = fmaf(W3_s[1 * W3_LD + c0 + j], h, p1);
+      p2 = fmaf(W3_s[2 * W3_LD + c0 + j], h, p2);
+    }
+  }
+  tc_fence_before();
+  if (half == 1) { sm.part[row * 3] = p0; sm.part[row * 3 + 1] = p1; sm.part[row * 3 + 2] = p2; }
+  __syncthreads();
+  if (half == 0) {
+    const float* vd = vd_of(row);
+    float s[3] = {p0 + sm.part[row * 3], p1 + sm.part[row * 3 + 1], p2 + sm.part[row * 3 + 2]};
+    if (vd) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        s[c] += W3_s[c * W3_LD + FC] * vd[0] + W3_s[c * W3_LD + FC + 1] * vd[1] +
+                W3_s[c * W3_LD + FC + 2] * vd[2];
+        s[c] += b3_s[c];
+        sm.rgb[row * 4 + c] = __fdiv_rn(1.0f, 1.0f + expf(-s[c]));
+      }
+    } else {
+      sm.rgb[row * 4] = sm.rgb[row * 4 + 1] = sm.rgb[row * 4 + 2] = 0.0f;
+    }
+  }
+  __syncthreads();
+}
+
+// CTA prologue shared by the kernels that shade: mbarriers, TMEM allocation, weight staging.
+// Returns the TMEM base address.  bars = {weights, layer 1, layer 2, tmem slot}.
+__device__ __forceinline__ uint32_t shade_prologue(unsigned char* prep_s, const float* prep_g,
+                                                   unsigned char* bars) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar_w = smem_u32(bars), bar1 = bar_w + 8, bar2 = bar_w + 16, slot = bar_w + 24;
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar1, 1);
+    mbar_init(bar2, 1);
+    constexpr uint32_t bytes = PREP_BYTES;
+    mbar_expect_tx(bar_w, bytes);
+    constexpr uint32_t CH = 32768;  // keep each bulk copy modest
+    for (uint32_t o = 0; o < bytes; o += CH)
+      tma_bulk_g2s(smem_u32(prep_s) + o, reinterpret_cast<const char*>(prep_g) + o,
+                   min(CH, bytes - o), bar_w);
+  }
+  if (warp == 0) tmem_alloc(slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *reinterpret_cast<volatile uint32_t*>(bars + 24);
 }
 
 // =================================================================================================
@@ -304,11 +516,8 @@ render_kernel(const FieldDev F, const BatchDev B) {
   extern __shared__ __align__(128) unsigned char smem[];
   const bool floater = B.floater_thresh > 0.0f;
   const SmemLayout L = smem_layout(F.S, floater);
-  float* prep_s = reinterpret_cast<float*>(smem + L.prep);
-  float* x_s = reinterpret_cast<float*>(smem + L.x);
-  float* part_s = x_s;  // layer-3 partial sums reuse the feature buffer
-  float* h_s = reinterpret_cast<float*>(smem + L.h);
-  float* rgb_s = reinterpret_cast<float*>(smem + L.rgb);
+  unsigned char* prep_s = smem + L.prep;
+  unsigned char* a_s = smem + L.a;
   int* sray_s = reinterpret_cast<int*>(smem + L.sray);
   float* sw_s = reinterpret_cast<float*>(smem + L.sw);
   float* w_all = reinterpret_cast<float*>(smem + L.w);
@@ -321,27 +530,20 @@ render_kernel(const FieldDev F, const BatchDev B) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = F.S, Sp = (S + 3) & ~3;
 
-  // -- stage the prepared MLP weights once per CTA with TMA bulk copies, and the z table ----------
-  if (tid == 0) {
-    mbar_init(mbar, 1);
-    constexpr uint32_t bytes = PREP_FLOATS * 4;
-    mbar_expect_tx(mbar, bytes);
-    constexpr uint32_t CH = 32768;  // keep each bulk copy modest
-    for (uint32_t o = 0; o < bytes; o += CH)
-      tma_bulk_g2s(smem_u32(prep_s) + o, reinterpret_cast<const char*>(F.prep) + o,
-                   min(CH, bytes - o), mbar);
-  }
+  // -- mbarriers, TMEM, TMA bulk staging of the weight operands (once per CTA), the z table --------
+  ShadeSmem sm;
+  sm.prep = prep_s;
+  sm.a = a_s;
+  sm.part = reinterpret_cast<float*>(smem + L.part);
+  sm.rgb = reinterpret_cast<float*>(smem + L.rgb);
+  sm.bar1 = mbar + 8;
+  sm.bar2 = mbar + 16;
   for (int k = tid; k < S; k += THREADS) z_s[k] = F.z[k];
   if (tid == 0) z_s[S] = F.z[S - 1];  // dist of the last sample = 0 (tensorBase.py:584-587)
-  __syncthreads();
+  sm.tmem = shade_prologue(prep_s, F.prep, smem + L.mbar);
   bool prep_ready = false;
-
-  const float* W1B_s = prep_s + PREP_W1B;
-  const float* W2T_s = prep_s + PREP_W2T;
-  const float* b1_s = prep_s + PREP_B1;
-  const float* b2_s = prep_s + PREP_B2;
-  const float* W3_s = prep_s + PREP_W3;
-  const float* b3_s = prep_s + PREP_B3;
+  uint32_t mma_phase = 0;
+  float* rgb_s = sm.rgb;
 
   float* w_s = w_all + warp * Sp;
   float* alpha_s = alpha_all + warp * Sp;
@@ -442,9 +644,9 @@ render_kernel(const FieldDev F, const BatchDev B) {
     // ============================ phase 2: appearance + MLP ======================================
     if (total > 0 && !prep_ready) { mbar_wait(mbar, 0); prep_ready = true; }
     for (int j0 = 0; j0 < total; j0 += TM) {
-      // -- gather: thread = (plane, sample) ------------------------------------------------------
-      if (tid < 3 * TM) {
-        const int pl = tid / TM, m = tid - pl * TM;
+      // -- gather: work item = (plane, sample); 24 products -> three 16-byte chunks of A1 hi/lo ----
+      for (int item = tid; item < 3 * TM; item += THREADS) {
+        const int pl = item / TM, m = item - pl * TM;
         const int j = j0 + m;
         float feat[CA];
         if (j < total) {
@@ -464,65 +666,19 @@ render_kernel(const FieldDev F, const BatchDev B) {
           if (pl == 0) { sray_s[m] = -1; sw_s[m] = 0.0f; }
         }
 #pragma unroll
-        for (int c = 0; c < CA; ++c) x_s[(pl * CA + c) * TM + m] = feat[c];
-      }
-      __syncthreads();
-      // -- layer 1 (basis folded in): h1 = relu(W1B^T x + b1) ------------------------------------
-      const int m0 = (tid & 15) * 4, n0 = (tid >> 4) * 8;
-      float acc[4][8];
-      cta_gemm<NF>(x_s, W1B_s, m0, n0, acc);
-#pragma unroll
-      for (int jn = 0; jn < 8; ++jn) {
-        const float b = b1_s[n0 + jn];
-        float4 v = make_float4(fmaxf(acc[0][jn] + b, 0.0f), fmaxf(acc[1][jn] + b, 0.0f),
-                               fmaxf(acc[2][jn] + b, 0.0f), fmaxf(acc[3][jn] + b, 0.0f));
-        *reinterpret_cast<float4*>(h_s + (n0 + jn) * TM + m0) = v;
-      }
-      __syncthreads();
-      // -- layer 2: h2 = relu(W2 h1 + b2), kept in registers; layer-3 partials --------------------
-      cta_gemm<FC>(h_s, W2T_s, m0, n0, acc);
-      {
-        float part[4][3];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) part[i][0] = part[i][1] = part[i][2] = 0.0f;
-#pragma unroll
-        for (int jn = 0; jn < 8; ++jn) {
-          const float b = b2_s[n0 + jn];
-          const float w30 = W3_s[0 * W3_LD + n0 + jn], w31 = W3_s[1 * W3_LD + n0 + jn],
-                      w32 = W3_s[2 * W3_LD + n0 + jn];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float h = fmaxf(acc[i][jn] + b, 0.0f);
-            part[i][0] = fmaf(w30, h, part[i][0]);
-            part[i][1] = fmaf(w31, h, part[i][1]);
-            part[i][2] = fmaf(w32, h, part[i][2]);
-          }
+        for (int c8 = 0; c8 < CA / 8; ++c8)
+          store_chunk(a_s, a_s + OPER1_BYTES, m, pl * (CA / 8) + c8, K1_CHUNKS, feat + 8 * c8);
+        if (pl == 0) {   // K padding 72..79 (the region is reused by A2, so re-zero every tile)
+          const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          store_chunk(a_s, a_s + OPER1_BYTES, m, K1_CHUNKS - 1, K1_CHUNKS, zero);
         }
-        const int tn = tid >> 4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) part_s[(tn * TM + m0 + i) * 3 + c] = part[i][c];
       }
-      __syncthreads();
-      // -- layer 3 tail: + view direction, bias, sigmoid (tensorBase.py:126-133) ------------------
-      if (tid < 3 * TM) {
-        const int m = tid / 3, c = tid - 3 * m;
-        float s = 0.0f;
-#pragma unroll
-        for (int tn = 0; tn < 16; ++tn) s += part_s[(tn * TM + m) * 3 + c];
+      // -- MLP on the tensor cores + layer 3 / sigmoid ---------------------------------------------
+      shade_tile(sm, mma_phase, [&](int m) -> const float* {
         const int r = sray_s[m];
-        if (r >= 0) {
-          const RaySm& Rr = ray_s[r];
-          s += W3_s[c * W3_LD + FC] * Rr.vd[0] + W3_s[c * W3_LD + FC + 1] * Rr.vd[1] +
-               W3_s[c * W3_LD + FC + 2] * Rr.vd[2];
-          s += b3_s[c];
-          rgb_s[m * 4 + c] = __fdiv_rn(1.0f, 1.0f + expf(-s));
-        } else {
-          rgb_s[m * 4 + c] = 0.0f;
-        }
-      }
-      __syncthreads();
+        return r >= 0 ? ray_s[r].vd : nullptr;
+      });
+      mma_phase ^= 1u;
       // -- composite: rgb_map += w * rgb, per ray in sample order (tensorBase.py:632) -------------
       if (tid < RT * 3) {
         const int r = tid / 3, c = tid - 3 * r;
@@ -568,34 +724,100 @@ render_kernel(const FieldDev F, const BatchDev B) {
     }
     __syncthreads();
   }
-  // never leave with the bulk copy still in flight
+  // never leave with the bulk copy still in flight; release TMEM
   if (!prep_ready) mbar_wait(mbar, 0);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(sm.tmem, TMEM_COLS);
+}
+
+// fused basis_mat + MLPRender_Fea_late_view on explicit plane x line products (one CTA per 128 rows)
+__global__ void __launch_bounds__(THREADS, 1)
+mlp_kernel(const float* __restrict__ prep_g, const float* __restrict__ feats,
+           const float* __restrict__ viewdirs, long long M, float* __restrict__ rgb) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SmemLayout L = smem_layout(MLP_S, false);
+  ShadeSmem sm;
+  sm.prep = smem + L.prep;
+  sm.a = smem + L.a;
+  sm.part = reinterpret_cast<float*>(smem + L.part);
+  sm.rgb = reinterpret_cast<float*>(smem + L.rgb);
+  const uint32_t mbar = smem_u32(smem + L.mbar);
+  sm.bar1 = mbar + 8;
+  sm.bar2 = mbar + 16;
+  float* vd_s = reinterpret_cast<float*>(smem + L.w);   // [TM][3] view directions (fits: MLP_S)
+  sm.tmem = shade_prologue(sm.prep, prep_g, smem + L.mbar);
+  mbar_wait(mbar, 0);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint32_t phase = 0;
+  const long long n_tiles = (M + TM - 1) / TM;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const long long base = t * TM;
+    for (int item = tid; item < 3 * TM; item += THREADS) {
+      const int pl = item / TM, m = item - pl * TM;
+      float feat[CA];
+#pragma unroll
+      for (int c = 0; c < CA; ++c)
+        feat[c] = (base + m < M) ? feats[(base + m) * NF + pl * CA + c] : 0.0f;
+#pragma unroll
+      for (int c8 = 0; c8 < CA / 8; ++c8)
+        store_chunk(sm.a, sm.a + OPER1_BYTES, m, pl * (CA / 8) + c8, K1_CHUNKS, feat + 8 * c8);
+      if (pl == 0) {
+        const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        store_chunk(sm.a, sm.a + OPER1_BYTES, m, K1_CHUNKS - 1, K1_CHUNKS, zero);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          vd_s[m * 3 + c] = (base + m < M) ? viewdirs[(base + m) * 3 + c] : 0.0f;
+      }
+    }
+    shade_tile(sm, phase, [&](int m) -> const float* { return vd_s + m * 3; });
+    phase ^= 1u;
+    for (int e = tid; e < TM * 3; e += THREADS) {
+      const int m = e / 3, c = e - 3 * m;
+      if (base + m < M) rgb[(base + m) * 3 + c] = sm.rgb[m * 4 + c];
+    }
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(sm.tmem, TMEM_COLS);
 }
 
 // ---- small kernels ------------------------------------------------------------------------------
-// prepared block: W1B = (W1 @ basis)^T, W2^T, biases, W3
+// prepared block: bf16 hi/lo operand images of W1B = W1 @ basis and W2, fp32 biases and W3
 __global__ void prepare_kernel(const float* __restrict__ basis, const float* __restrict__ w1,
                                const float* __restrict__ b1, const float* __restrict__ w2,
                                const float* __restrict__ b2, const float* __restrict__ w3,
-                               const float* __restrict__ b3, float* __restrict__ prep) {
+                               const float* __restrict__ b3, unsigned char* __restrict__ prep) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int stride = gridDim.x * blockDim.x;
-  for (int e = t; e < NF * FC; e += stride) {
-    const int k = e / FC, n = e - k * FC;
+  for (int e = t; e < FC * K1; e += stride) {
+    const int n = e / K1, k = e - n * K1;
     float s = 0.0f;
-    for (int j = 0; j < APP_DIM; ++j) s = fmaf(w1[n * APP_DIM + j], basis[j * NF + k], s);
-    prep[PREP_W1B + e] = s;
+    if (k < NF)
+      for (int j = 0; j < APP_DIM; ++j) s = fmaf(w1[n * APP_DIM + j], basis[j * NF + k], s);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(s);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(s - __bfloat162float(hi));
+    const int off = oper_offset(n, k, K1_CHUNKS);
+    *reinterpret_cast<__nv_bfloat16*>(prep + PREP_B1HI + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(prep + PREP_B1LO + off) = lo;
   }
   for (int e = t; e < FC * FC; e += stride) {
-    const int k = e / FC, n = e - k * FC;
-    prep[PREP_W2T + e] = w2[n * FC + k];
+    const int n = e / FC, k = e - n * FC;
+    const float s = w2[n * FC + k];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(s);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(s - __bfloat162float(hi));
+    const int off = oper_offset(n, k, K2_CHUNKS);
+    *reinterpret_cast<__nv_bfloat16*>(prep + PREP_B2HI + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(prep + PREP_B2LO + off) = lo;
   }
-  for (int e = t; e < FC; e += stride) { prep[PREP_B1 + e] = b1[e]; prep[PREP_B2 + e] = b2[e]; }
+  float* tail = reinterpret_cast<float*>(prep + PREP_TAIL);
+  for (int e = t; e < FC; e += stride) { tail[TAIL_B1 + e] = b1[e]; tail[TAIL_B2 + e] = b2[e]; }
   for (int e = t; e < 3 * W3_LD; e += stride) {
     const int c = e / W3_LD, n = e - c * W3_LD;
-    prep[PREP_W3 + e] = n < FC + 3 ? w3[c * (FC + 3) + n] : 0.0f;
+    tail[TAIL_W3 + e] = n < FC + 3 ? w3[c * (FC + 3) + n] : 0.0f;
   }
-  for (int e = t; e < 4; e += stride) prep[PREP_B3 + e] = e < 3 ? b3[e] : 0.0f;
+  for (int e = t; e < 4; e += stride) tail[TAIL_B3 + e] = e < 3 ? b3[e] : 0.0f;
 }
 
 __global__ void density_feature_kernel(const FieldDev F, const float* __restrict__ xyz,
@@ -654,8 +876,25 @@ cudaError_t launch_render(const FieldDev& F, const BatchDev& B, int n_sms, cudaS
   return cudaGetLastError();
 }
 
+cudaError_t launch_mlp(const float* prep, const float* feats, const float* viewdirs, long long M,
+                       float* rgb, int n_sms, cudaStream_t stream) {
+  if (M == 0) return cudaSuccess;
+  const size_t smem = render_smem_bytes(MLP_S, false);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  long long n_tiles = (M + TM - 1) / TM;
+  int grid = (int)(n_tiles < n_sms ? n_tiles : n_sms);
+  mlp_kernel<<<grid, THREADS, smem, stream>>>(prep, feats, viewdirs, M, rgb);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_prepare(const float* basis, const float* w1, const float* b1, const float* w2,
-                           const float* b2, const float* w3, const float* b3, float* prep,
+                           const float* b2, const float* w3, const float* b3, unsigned char* prep,
                            cudaStream_t stream) {
   prepare_kernel<<<64, 256, 0, stream>>>(basis, w1, b1, w2, b2, w3, b3, prep);
   return cudaGetLastError();

@@ -303,11 +303,26 @@ class TensorBase(torch.nn.Module):
         """(Re)builds the folded / re-laid-out MLP block the kernel stages into shared memory."""
         dev = self.basis_mat.weight.device
         if self._prepared is None or self._prepared.device != dev:
-            n = _lib.lib().lrf_prepared_bytes() // 4
-            self._prepared = torch.empty(n, dtype=torch.float32, device=dev)
+            n = _lib.lib().lrf_prepared_bytes()
+            self._prepared = torch.empty(n, dtype=torch.uint8, device=dev)
         _lib.check(_lib.lib().lrf_field_prepare(C.byref(field_struct), _ptr(self._prepared),
                                                 _stream(dev)))
         return self._prepared
+
+    def shade_products(self, products, viewdirs):
+        """basis_mat + renderModule on explicit plane x line products [M,72] and normalised view
+        directions [M,3] -> rgb [M,3]; the tensor-core MLP of the render kernel on its own."""
+        _require_cuda(products, "products")
+        dev = products.device
+        x = products.detach().to(torch.float32).contiguous()
+        v = viewdirs.detach().to(dev, torch.float32).contiguous()
+        out = torch.empty(x.shape[0], 3, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            fs, keep = self._field_struct(None)
+            prep = self.prepare(fs)
+            _lib.check(_lib.lib().lrf_mlp_forward(_ptr(prep), _ptr(x), _ptr(v), x.shape[0],
+                                                  _ptr(out), _stream(dev)))
+        return out
 
     def _check_no_autograd(self, *tensors):
         if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):

@@ -64,6 +64,25 @@ def test_feature_entry_points(cfg1):
     assert rel_err(a, g["unit.app_feature"], floor=1e-2) < TOL
 
 
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 5000])
+def test_tensor_core_mlp_vs_torch_fp32(cfg1, n):
+    """The tcgen05 MLP (bf16 hi/lo split, three products per layer) against plain torch fp32."""
+    g, m = cfg1
+    gen = torch.Generator().manual_seed(n)
+    prod = (0.1 * torch.randn(n, 72, generator=gen)) * (0.1 * torch.randn(n, 72, generator=gen))
+    prod[0] *= 50.0                                          # one large-magnitude row
+    vd = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        out = m.shade_products(prod.cuda(), vd.cuda()).cpu()
+        feat = prod @ sd["basis_mat.weight"].t()
+        h = torch.relu(feat @ sd["renderModule.mlp.0.weight"].t() + sd["renderModule.mlp.0.bias"])
+        h = torch.relu(h @ sd["renderModule.mlp.2.weight"].t() + sd["renderModule.mlp.2.bias"])
+        ref = torch.sigmoid(torch.cat([h, vd], -1) @ sd["renderModule.mlp_view.0.weight"].t()
+                            + sd["renderModule.mlp_view.0.bias"])
+    assert rel_err(out.numpy(), ref.numpy()) < 2e-5
+
+
 @pytest.mark.parametrize("name,cases", [
     ("opaque_32", [("eval", {}), ("eval_floater", dict(floater_thresh=0.5))]),
     ("relu_32", [("eval", {})]),
