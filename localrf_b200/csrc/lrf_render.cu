@@ -30,7 +30,11 @@ constexpr int NWARPS = THREADS / 32;
 constexpr int RT = NWARPS;   // rays per tile
 constexpr int TM = 128;      // appearance samples per MLP sub-tile (= UMMA M)
 constexpr int MLP_S = 192;       // pseudo sample count sizing mlp_kernel's scratch (>= TM*3*4 bytes)
-constexpr int TMEM_COLS = 256;   // acc1 [0,128) + acc2 [128,256) fp32 columns
+constexpr int TMEM_COLS = 512;   // power of two >= 384 used columns
+constexpr int TM_ACC1 = 0;       // fp32 accumulator of layer 1   [0,128)
+constexpr int TM_ACC2 = 128;     // fp32 accumulator of layer 2   [128,256)
+constexpr int TM_A2HI = 256;     // layer-2 A operand, bf16 hi: 128 K-elements = 64 columns
+constexpr int TM_A2LO = 320;     // layer-2 A operand, bf16 lo
 // tcgen05 instruction descriptor, kind::f16: D=f32 (bit4), A=B=bf16 (bits 7,10), both K-major,
 // N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FC >> 3) << 17) |
@@ -61,7 +65,7 @@ __host__ __device__ inline SmemLayout smem_layout(int S, bool floater) {
   int Sp = (S + 3) & ~3;
   L.prep = off;  off += PREP_BYTES;               // B operands (bf16 hi/lo) + fp32 tail
   off = (off + 1023) & ~1023;
-  L.a = off;     off += 2 * OPER2_BYTES;          // A2 hi/lo; A1 hi/lo alias its start
+  L.a = off;     off += 2 * OPER1_BYTES;          // A1 hi/lo (layer-2's A operand lives in TMEM)
   L.part = off;  off += TM * 3 * 4;               // layer-3 partial sums of the upper column half
   L.rgb = off;   off += TM * 4 * 4;
   L.sray = off;  off += TM * 4;
@@ -146,6 +150,29 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in TMEM (lane = row, 32-bit column c = K elements 2c, 2c+1)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns from registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),
+        "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
@@ -203,6 +230,23 @@ __device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_hi, uint
     umma_bf16(d_tmem, ah, bh, acc);
     umma_bf16(d_tmem, ah, bl, 1u);
     umma_bf16(d_tmem, al, bh, 1u);
+    acc = 1u;
+  }
+  umma_commit(bar);
+}
+
+// Layer 2: A (hi/lo) in TMEM, B in shared memory.
+__device__ __forceinline__ void issue_layer_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo,
+                                               uint32_t b_hi, uint32_t b_lo, int ksteps, int chunks,
+                                               uint32_t bar) {
+  const uint32_t sbo = (uint32_t)chunks * 128u;
+  uint32_t acc = 0;
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint32_t ko = (uint32_t)ks * 256u, kc = (uint32_t)ks * 8u;   // 16 bf16 = 8 TMEM columns
+    const uint64_t bh = umma_desc(b_hi + ko, 128u, sbo), bl = umma_desc(b_lo + ko, 128u, sbo);
+    umma_bf16_ts(d_tmem, a_hi + kc, bh, acc);
+    umma_bf16_ts(d_tmem, a_hi + kc, bl, 1u);
+    umma_bf16_ts(d_tmem, a_lo + kc, bh, 1u);
     acc = 1u;
   }
   umma_commit(bar);
@@ -408,21 +452,19 @@ __device__ __forceinline__ void shade_tile(const ShadeSmem& sm, uint32_t phase, 
   const float* W3_s = tail + TAIL_W3;
   const float* b3_s = tail + TAIL_B3;
   const uint32_t prep_a = smem_u32(sm.prep), a_a = smem_u32(sm.a);
-  unsigned char* a2_hi = sm.a;
-  unsigned char* a2_lo = sm.a + OPER2_BYTES;
 
   // A1 was written with generic-proxy stores: make it visible to the tensor core, then sync
   fence_async_smem();
   __syncthreads();
   if (tid == 0) {
     tc_fence_after();
-    issue_layer(sm.tmem, a_a, a_a + OPER1_BYTES, prep_a + PREP_B1HI, prep_a + PREP_B1LO,
+    issue_layer(sm.tmem + TM_ACC1, a_a, a_a + OPER1_BYTES, prep_a + PREP_B1HI, prep_a + PREP_B1LO,
                 K1 / 16, K1_CHUNKS, sm.bar1);
   }
   mbar_wait(sm.bar1, phase);
   tc_fence_after();
 
-  // -- epilogue 1: h1 = relu(acc1 + b1) -> bf16 hi/lo A operand of layer 2 ------------------------
+  // -- epilogue 1: h1 = relu(acc1 + b1) -> bf16 hi/lo A operand of layer 2, written to TMEM ---------
   const int q = warp & 3, half = warp >> 2;       // TMEM lane quarter, column half
   const int row = q * 32 + lane;
   const uint32_t t_row = sm.tmem + ((uint32_t)(q * 32) << 16);
@@ -430,22 +472,24 @@ __device__ __forceinline__ void shade_tile(const ShadeSmem& sm, uint32_t phase, 
   for (int cc = 0; cc < 2; ++cc) {
     const int c0 = half * 64 + cc * 32;
     float v[32];
-    tmem_ld32(t_row + (uint32_t)c0, v);
+    tmem_ld32(t_row + (uint32_t)(TM_ACC1 + c0), v);
+    uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      float h[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) h[e] = fmaxf(v[j + e] + b1_s[c0 + j + e], 0.0f);
-      store_chunk(a2_hi, a2_lo, row, (c0 + j) >> 3, K2_CHUNKS, h);
+    for (int j = 0; j < 16; ++j) {
+      const float x0 = fmaxf(v[2 * j] + b1_s[c0 + 2 * j], 0.0f);
+      const float x1 = fmaxf(v[2 * j + 1] + b1_s[c0 + 2 * j + 1], 0.0f);
+      split2(x0, x1, hi[j], lo[j]);
     }
+    tmem_st16(t_row + (uint32_t)(TM_A2HI + c0 / 2), hi);
+    tmem_st16(t_row + (uint32_t)(TM_A2LO + c0 / 2), lo);
   }
-  fence_async_smem();
+  tmem_st_wait();
   tc_fence_before();
   __syncthreads();
   if (tid == 0) {
     tc_fence_after();
-    issue_layer(sm.tmem + FC, a_a, a_a + OPER2_BYTES, prep_a + PREP_B2HI, prep_a + PREP_B2LO,
-                FC / 16, K2_CHUNKS, sm.bar2);
+    issue_layer_ts(sm.tmem + TM_ACC2, sm.tmem + TM_A2HI, sm.tmem + TM_A2LO, prep_a + PREP_B2HI,
+                   prep_a + PREP_B2LO, FC / 16, K2_CHUNKS, sm.bar2);
   }
   mbar_wait(sm.bar2, phase);
   tc_fence_after();
@@ -456,7 +500,7 @@ __device__ __forceinline__ void shade_tile(const ShadeSmem& sm, uint32_t phase, 
   for (int cc = 0; cc < 2; ++cc) {
     const int c0 = half * 64 + cc * 32;
     float v[32];
-    tmem_ld32(t_row + (uint32_t)(FC + c0), v);
+    tmem_ld32(t_row + (uint32_t)(TM_ACC2 + c0), v);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float h = fmaxf(v[j] + b2_s[c0 + j], 0.0f);
