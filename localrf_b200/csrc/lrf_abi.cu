@@ -8,9 +8,10 @@
 #include "lrf_common.cuh"
 
 namespace lrf {
-size_t render_smem_bytes(int S, bool floater);
+size_t render_smem_bytes(int S, bool floater, int max_smem);
 int render_threads();
-cudaError_t launch_render(const FieldDev& F, const BatchDev& B, int n_sms, cudaStream_t stream);
+cudaError_t launch_render(const FieldDev& F, const BatchDev& B, int n_sms, int max_smem,
+                          cudaStream_t stream);
 cudaError_t launch_prepare(const float* basis, const float* w1, const float* b1, const float* w2,
                            const float* b2, const float* w3, const float* b3, unsigned char* prep,
                            cudaStream_t stream);
@@ -41,7 +42,10 @@ struct DevInfo {
   int n_sms = 0;
   int max_smem = 0;
   bool ok = false;
+  unsigned long long* sched = nullptr;   // ring of per-launch ray counters (device memory)
+  unsigned int next = 0;
 };
+constexpr unsigned int SCHED_RING = 256;
 
 int device_info(DevInfo& d) {
   static thread_local DevInfo cache[64];
@@ -55,8 +59,11 @@ int device_info(DevInfo& d) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
     cache[dev].n_sms = p.multiProcessorCount;
     cache[dev].max_smem = (int)p.sharedMemPerBlockOptin;
+    e = cudaMalloc(&cache[dev].sched, SCHED_RING * sizeof(unsigned long long));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(ray counters)");
     cache[dev].ok = true;
   }
+  cache[dev].next = (cache[dev].next + 1) % SCHED_RING;
   d = cache[dev];
   return LRF_OK;
 }
@@ -185,10 +192,11 @@ int lrf_render(const LrfField* f, const void* prepared, const LrfBatch* b, const
   DevInfo d;
   rc = device_info(d);
   if (rc != LRF_OK) return rc;
-  const size_t smem = lrf::render_smem_bytes(F.S, B.floater_thresh > 0.0f);
+  const size_t smem = lrf::render_smem_bytes(F.S, B.floater_thresh > 0.0f, d.max_smem);
   if ((long long)smem > d.max_smem)
     return fail(LRF_ERR_UNSUPPORTED, "sample table too long for the shared-memory budget");
-  cudaError_t e = lrf::launch_render(F, B, d.n_sms, (cudaStream_t)stream);
+  B.sched = d.sched + d.next;
+  cudaError_t e = lrf::launch_render(F, B, d.n_sms, d.max_smem, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "render_kernel");
   return LRF_OK;
 }
@@ -244,7 +252,7 @@ int lrf_launch_info(int32_t* n_sms, int32_t* threads_per_cta, int32_t* smem_byte
   if (rc != LRF_OK) return rc;
   if (n_sms) *n_sms = d.n_sms;
   if (threads_per_cta) *threads_per_cta = lrf::render_threads();
-  if (smem_bytes_per_cta) *smem_bytes_per_cta = (int32_t)lrf::render_smem_bytes(344, false);
+  if (smem_bytes_per_cta) *smem_bytes_per_cta = (int32_t)lrf::render_smem_bytes(344, false, d.max_smem);
   return LRF_OK;
 }
 

@@ -80,6 +80,7 @@ struct BatchDev {
   float* weights;
   float* dirs;
   unsigned long long* stats;
+  unsigned long long* sched;   // ray counter of this launch (library-owned, zeroed per launch)
 };
 
 // ---- sampling helpers -------------------------------------------------------------------------
