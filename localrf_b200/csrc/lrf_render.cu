@@ -29,6 +29,8 @@
 //       output (white background, blend, accumulate, exposure, clamp).
 //
 // The weight operands are staged once per CTA by TMA bulk copies (cp.async.bulk -> UBLKCP).
+#include <cstdlib>
+
 #include "lrf_device.cuh"
 
 namespace lrf {
@@ -52,8 +54,9 @@ struct Slot {                       // one ray in flight between a producer and 
 };
 
 struct Ctrl {                       // CTA control block in shared memory
-  unsigned long long bar_w, full[2], free_[2], mma1, a2rdy, mma2;
+  unsigned long long bar_w, full[2], mma1, a2rdy, mma2;
   uint32_t tmem;
+  unsigned int released;            // tiles whose A1 buffer + row metadata may be overwritten
   unsigned int cursor;              // rows handed out so far (tile = cursor >> 7)
   unsigned int prod_done;
   unsigned int n_tiles_final;
@@ -166,13 +169,13 @@ struct ProdCtx {
   int lane;
 };
 
-// wait until buffer (T & 1) may be rewritten for tile T (its previous use T-2 has been read by the
-// tensor core and its row metadata by the consumers)
+// wait until buffer (T & 1) may be rewritten for tile T: tile T-2 has been read by the tensor core
+// and its row metadata by the consumers.  A monotonic counter, not an mbarrier parity: producers
+// can be more than two tiles ahead of the consumers, which a 1-bit phase cannot express.
 __device__ __forceinline__ void wait_tile_free(Ctrl* ctrl, unsigned int T) {
   if (T >= 2) {
-    const uint32_t bar = smem_u32(&ctrl->free_[T & 1]);
-    const uint32_t parity = ((T >> 1) - 1) & 1;
-    while (!mbar_try(bar, parity)) { }
+    while (*reinterpret_cast<volatile unsigned int*>(&ctrl->released) + 1u < T) { }
+    __threadfence_block();
   }
 }
 
@@ -272,12 +275,11 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
     mbar_init(smem_u32(&ctrl->bar_w), 1);
     mbar_init(smem_u32(&ctrl->full[0]), TM);
     mbar_init(smem_u32(&ctrl->full[1]), TM);
-    mbar_init(smem_u32(&ctrl->free_[0]), TM + 1);   // tcgen05.commit + the 128 consumer threads
-    mbar_init(smem_u32(&ctrl->free_[1]), TM + 1);
     mbar_init(smem_u32(&ctrl->mma1), 1);
     mbar_init(smem_u32(&ctrl->a2rdy), TM);
     mbar_init(smem_u32(&ctrl->mma2), 1);
     ctrl->cursor = 0; ctrl->prod_done = 0; ctrl->n_tiles_final = 0; ctrl->done = 0;
+    ctrl->released = 0;
     constexpr uint32_t bytes = PREP_BYTES;
     mbar_expect_tx(smem_u32(&ctrl->bar_w), bytes);
     constexpr uint32_t CH = 32768;
@@ -462,7 +464,6 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
           umma_bf16(tmem + TM_ACC1, al, bh, 1u);
           accf = 1u;
         }
-        umma_commit(smem_u32(&ctrl->free_[b]));      // A1 tile consumed by the tensor core
         umma_commit(smem_u32(&ctrl->mma1));
       }
       __syncwarp();
@@ -497,7 +498,11 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
       // row metadata -> registers, then the A1 tile (and its metadata) may be rewritten
       const int my_slot = smem[L.mslot + b * TM + row];
       const float my_w = reinterpret_cast<const float*>(smem + L.mw)[b * TM + row];
-      mbar_arrive(smem_u32(&ctrl->free_[b]));
+      asm volatile("bar.sync 2, 128;" ::: "memory");   // MMA1(T) done + all metadata read ->
+      if (ctid == 0) {                                  // the A1 buffer of tile T is free again
+        __threadfence_block();
+        *reinterpret_cast<volatile unsigned int*>(&ctrl->released) = T + 1u;
+      }
       // -- epilogue 1: h1 = relu(acc1 + b1) -> bf16 hi/lo, layer 2's A operand in TMEM -------------
 #pragma unroll 1
       for (int c0 = 0; c0 < FC; c0 += 32) {
@@ -577,7 +582,12 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
 int render_threads() { return THREADS; }
 
 static int pick_nprod(int S, bool floater, int max_smem) {
-  for (int n = MAX_PROD; n >= 1; --n)
+  int cap = MAX_PROD;
+  if (const char* e = getenv("LRF_NPROD")) {      // tuning / debugging knob
+    const int v = atoi(e);
+    if (v >= 1 && v < cap) cap = v;
+  }
+  for (int n = cap; n >= 1; --n)
     if (smem_v3(S, floater, n).total <= max_smem) return n;
   return 0;
 }
