@@ -43,10 +43,17 @@ constexpr int NSLOT = 3;            // ray slots per producer warp
 constexpr int QCAP = 64;            // per-warp queue of selected samples
 constexpr int SPIN_PAD = 2048;      // polls before a blocked producer pads the open tile
 
+// colour accumulators are 32-bit fixed point (2^-30 units, 9.3e-10: finer than an fp32 ulp of the
+// sums, which are <= 1): integer adds are associative, so the rows of a ray can be composited in any
+// order, by any thread, and the result is bit-identical.  (32-bit shared-memory atomics are native;
+// 64-bit ones turn into contended CAS loops.)
+constexpr float FIX_SCALE = 1073741824.0f;              // 2^30
+constexpr float FIX_INV = 1.0f / 1073741824.0f;
+
 struct Slot {                       // one ray in flight between a producer and the consumers
   float vd[3];
   float blend;
-  float rgb[3];
+  unsigned int rgb[3];              // sum of w * rgb, fixed point
   float acc;
   long long ray;
   int pending;                      // 1 (open token) + rows submitted and not yet composited
@@ -64,7 +71,7 @@ struct Ctrl {                       // CTA control block in shared memory
 };
 
 struct SmemV3 {
-  int prep, a1, mslot, mw, crow, slots, q, alpha, z, ctrl, total;
+  int prep, a1, mslot, mw, slots, q, alpha, z, ctrl, total;
   int per_prod;                     // bytes of one producer's queue (+ alpha table)
 };
 
@@ -77,7 +84,7 @@ __host__ __device__ inline SmemV3 smem_v3(int S, bool floater, int nprod) {
   L.a1 = off;     off += 2 * 2 * OPER1_BYTES;          // two A1 tiles (hi + lo each)
   L.mslot = off;  off += 2 * TM;                        // per-row slot id (u8), two tiles
   L.mw = off;     off += 2 * TM * 4;                    // per-row weight
-  L.crow = off;   off += TM * 16;                       // w*rgb + slot id per row of the tile in flight
+  off = (off + 15) & ~15;
   L.slots = off;  off += MAX_PROD * NSLOT * (int)sizeof(Slot);
   L.q = off;
   L.per_prod = QCAP * 2 + QCAP * 4 + (floater ? Sp * 4 : 0);
@@ -92,12 +99,15 @@ __host__ __device__ inline SmemV3 smem_v3(int S, bool floater, int nprod) {
 }
 
 // ---- outputs (local_tensorfs.py:467-497) --------------------------------------------------------
-__device__ __forceinline__ void write_rgb(const BatchDev& B, long long r, const float* rgb_acc,
-                                          float acc, float blend) {
+__device__ __forceinline__ void write_rgb(const BatchDev& B, long long r,
+                                          const unsigned int* rgb_fix, float acc, float blend) {
   float c[3];
   const float bg = B.white_bg ? (1.0f - acc) : 0.0f;              // tensorBase.py:633-634
 #pragma unroll
-  for (int a = 0; a < 3; ++a) c[a] = (rgb_acc[a] + bg) * blend;
+  for (int a = 0; a < 3; ++a) {
+    const unsigned int v = *reinterpret_cast<const volatile unsigned int*>(rgb_fix + a);
+    c[a] = (__uint2float_rn(v) * FIX_INV + bg) * blend;           // tensorBase.py:632
+  }
   if (B.accumulate) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) c[a] = B.rgb[3 * r + a] + c[a];
@@ -337,7 +347,7 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
       if (lane == 0) {
         slot->vd[0] = R.vd[0]; slot->vd[1] = R.vd[1]; slot->vd[2] = R.vd[2];
         slot->blend = R.blend;
-        slot->rgb[0] = slot->rgb[1] = slot->rgb[2] = 0.0f;
+        slot->rgb[0] = slot->rgb[1] = slot->rgb[2] = 0u;
         slot->ray = ray;
         slot->pending = 1;
         __threadfence_block();
@@ -484,7 +494,6 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
     const float* b2_s = tail + TAIL_B2;
     const float* W3_s = tail + TAIL_W3;
     const float* b3_s = tail + TAIL_B3;
-    float4* crow = reinterpret_cast<float4*>(smem + L.crow);
     mbar_wait(smem_u32(&ctrl->bar_w), 0);
     for (unsigned int T = 0;; ++T) {
       const int b = (int)(T & 1);
@@ -510,10 +519,11 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
         tmem_ld32(t_row + (uint32_t)(TM_ACC1 + c0), v);
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float x0 = fmaxf(v[2 * j] + b1_s[c0 + 2 * j], 0.0f);
-          const float x1 = fmaxf(v[2 * j + 1] + b1_s[c0 + 2 * j + 1], 0.0f);
-          split2(x0, x1, hi[j], lo[j]);
+        for (int j = 0; j < 16; j += 2) {
+          const float4 bb = *reinterpret_cast<const float4*>(b1_s + c0 + 2 * j);
+          split2(fmaxf(v[2 * j] + bb.x, 0.0f), fmaxf(v[2 * j + 1] + bb.y, 0.0f), hi[j], lo[j]);
+          split2(fmaxf(v[2 * j + 2] + bb.z, 0.0f), fmaxf(v[2 * j + 3] + bb.w, 0.0f), hi[j + 1],
+                 lo[j + 1]);
         }
         tmem_st16(t_row + (uint32_t)(TM_A2HI + c0 / 2), hi);
         tmem_st16(t_row + (uint32_t)(TM_A2LO + c0 / 2), lo);
@@ -524,52 +534,40 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
       // -- epilogue 2: h2 = relu(acc2 + b2); layer 3 + sigmoid (tensorBase.py:126-133) ---------------
       mbar_wait(smem_u32(&ctrl->mma2), T & 1);
       tc_fence_after();
-      float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
+      float pa[3] = {0.0f, 0.0f, 0.0f}, pb[3] = {0.0f, 0.0f, 0.0f};   // two chains per channel (ILP)
 #pragma unroll 1
       for (int c0 = 0; c0 < FC; c0 += 32) {
         float v[32];
         tmem_ld32(t_row + (uint32_t)(TM_ACC2 + c0), v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float h = fmaxf(v[j] + b2_s[c0 + j], 0.0f);
-          p0 = fmaf(W3_s[0 * W3_LD + c0 + j], h, p0);
-          p1 = fmaf(W3_s[1 * W3_LD + c0 + j], h, p1);
-          p2 = fmaf(W3_s[2 * W3_LD + c0 + j], h, p2);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(b2_s + c0 + j);
+          const float h0 = fmaxf(v[j] + bb.x, 0.0f), h1 = fmaxf(v[j + 1] + bb.y, 0.0f);
+          const float h2 = fmaxf(v[j + 2] + bb.z, 0.0f), h3 = fmaxf(v[j + 3] + bb.w, 0.0f);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float4 ww = *reinterpret_cast<const float4*>(W3_s + c * W3_LD + c0 + j);
+            pa[c] = fmaf(ww.x, h0, pa[c]); pb[c] = fmaf(ww.y, h1, pb[c]);
+            pa[c] = fmaf(ww.z, h2, pa[c]); pb[c] = fmaf(ww.w, h3, pb[c]);
+          }
         }
       }
       tc_fence_before();
-      float4 cr = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(my_slot));
+      // -- composite (tensorBase.py:632): w * rgb into the ray's fixed-point accumulators -------------
       if (my_slot != 0xFF) {
-        const Slot* sl = slots + my_slot;
-        float s[3] = {p0, p1, p2};
+        Slot* sl = slots + my_slot;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          s[c] += W3_s[c * W3_LD + FC] * sl->vd[0] + W3_s[c * W3_LD + FC + 1] * sl->vd[1] +
-                  W3_s[c * W3_LD + FC + 2] * sl->vd[2];
-          s[c] += b3_s[c];
-          s[c] = __fdiv_rn(1.0f, 1.0f + expf(-s[c]));
+          float sc = pa[c] + pb[c];
+          sc += W3_s[c * W3_LD + FC] * sl->vd[0] + W3_s[c * W3_LD + FC + 1] * sl->vd[1] +
+                W3_s[c * W3_LD + FC + 2] * sl->vd[2];
+          sc += b3_s[c];
+          sc = __fdiv_rn(1.0f, 1.0f + expf(-sc));
+          atomicAdd(&sl->rgb[c], __float2uint_rn(my_w * sc * FIX_SCALE));
         }
-        cr.x = my_w * s[0]; cr.y = my_w * s[1]; cr.z = my_w * s[2];
-      }
-      crow[row] = cr;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      // -- composite: one thread per (slot, channel), rows in order (tensorBase.py:632) --------------
-      int n_mine = 0;
-      const int cs = ctid / 3, cc = ctid - 3 * cs;
-      if (ctid < nprod * NSLOT * 3 && *reinterpret_cast<volatile int*>(&slots[cs].state) == 1) {
-        float a = slots[cs].rgb[cc];
-        const float* cf = reinterpret_cast<const float*>(crow);
-#pragma unroll 4
-        for (int m = 0; m < TM; ++m) {
-          if (__float_as_int(cf[4 * m + 3]) == cs) { a += cf[4 * m + cc]; ++n_mine; }
-        }
-        if (n_mine) slots[cs].rgb[cc] = a;
-      }
-      __threadfence_block();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (ctid < nprod * NSLOT * 3 && cc == 0 && n_mine > 0) {
-        const int old = atomicSub(&slots[cs].pending, n_mine);
-        if (old == n_mine) finalize_slot(B, slots + cs);
+        __threadfence_block();
+        const int old = atomicSub(&sl->pending, 1);
+        if (old == 1) { __threadfence_block(); finalize_slot(B, sl); }
       }
     }
     tc_fence_before();
