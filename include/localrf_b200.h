@@ -107,6 +107,10 @@ typedef struct LrfOutputs {
   float *depth;               /* [n_rays] */
   float *weights;             /* optional [n_rays][n_samples]: final per-sample weights of this field */
   float *directions;          /* optional [n_rays][3]: camera-space directions (ray-generation mode) */
+  int64_t *ij;                /* optional [n_rays][2]: pixel (col, row) of every ray id (ray-generation mode) */
+  float *pix;                 /* optional [n_rays][4]: when set, rgb and depth are written interleaved
+                                 here (r,g,b,depth) instead of to rgb/depth -- the layout the multi-GPU
+                                 path all-gathers in one collective */
   unsigned long long *stats;  /* optional [2]: += {density samples marched, appearance samples shaded} */
 } LrfOutputs;
 

@@ -10,8 +10,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_CSRC, "liblrf_b200.so")
-SOURCES = ["lrf_render.cu", "lrf_abi.cu"]
-HEADERS = ["lrf_common.cuh", os.path.join("..", "..", "include", "localrf_b200.h")]
+SOURCES = ["lrf_render.cu", "lrf_aux.cu", "lrf_abi.cu"]
+HEADERS = ["lrf_common.cuh", "lrf_device.cuh", os.path.join("..", "..", "include", "localrf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -61,7 +61,7 @@ class LrfBatch(C.Structure):
 
 class LrfOutputs(C.Structure):
     _fields_ = [("rgb", _vp), ("depth", _vp), ("weights", _vp), ("directions", _vp),
-                ("stats", _vp)]
+                ("ij", _vp), ("pix", _vp), ("stats", _vp)]
 
 
 EXPORTS = ["lrf_version", "lrf_last_error", "lrf_prepared_bytes", "lrf_field_prepare",

@@ -157,7 +157,7 @@ int lrf_render(const LrfField* f, const void* prepared, const LrfBatch* b, const
   if (rc != LRF_OK) return rc;
   if (b->n_rays < 0) return fail(LRF_ERR_INVALID, "n_rays < 0");
   if (b->n_rays == 0) return LRF_OK;
-  if (!o->rgb || !o->depth) return fail(LRF_ERR_INVALID, "rgb/depth output is NULL");
+  if (!o->pix && (!o->rgb || !o->depth)) return fail(LRF_ERR_INVALID, "rgb/depth output is NULL");
   lrf::BatchDev B;
   memset(&B, 0, sizeof(B));
   B.n_rays = b->n_rays;
@@ -186,8 +186,14 @@ int lrf_render(const LrfField* f, const void* prepared, const LrfBatch* b, const
   B.exposure = b->exposure;
   B.accumulate = b->accumulate; B.finalize = b->finalize; B.white_bg = b->white_bg;
   B.floater_thresh = b->floater_thresh;
-  B.rgb = o->rgb; B.depth = o->depth; B.weights = o->weights;
+  if (o->pix) {
+    B.rgb = o->pix; B.depth = o->pix + 3; B.rgb_stride = 4; B.depth_stride = 4;
+  } else {
+    B.rgb = o->rgb; B.depth = o->depth; B.rgb_stride = 3; B.depth_stride = 1;
+  }
+  B.weights = o->weights;
   B.dirs = b->rays ? nullptr : o->directions;
+  B.ij = b->rays ? nullptr : reinterpret_cast<long long*>(o->ij);
   B.stats = o->stats;
   DevInfo d;
   rc = device_info(d);

@@ -77,8 +77,10 @@ struct BatchDev {
   float floater_thresh;
   float* rgb;
   float* depth;
+  int rgb_stride, depth_stride;   // floats between consecutive rays (3 / 1, or 4 / 4 for pix)
   float* weights;
   float* dirs;
+  long long* ij;
   unsigned long long* stats;
   unsigned long long* sched;   // ray counter of this launch (library-owned, zeroed per launch)
 };

@@ -248,6 +248,7 @@ __device__ __forceinline__ void setup_ray(const BatchDev& B, long long r, RaySm&
       dc[2] = -1.0f;
     }
     if (B.dirs) { B.dirs[3 * r] = dc[0]; B.dirs[3 * r + 1] = dc[1]; B.dirs[3 * r + 2] = dc[2]; }
+    if (B.ij) { B.ij[2 * r] = col; B.ij[2 * r + 1] = row; }
     const float* c = B.c2w + 12 * view;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {                                 // get_rays_lean

@@ -110,7 +110,7 @@ __device__ __forceinline__ void write_rgb(const BatchDev& B, long long r,
   }
   if (B.accumulate) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) c[a] = B.rgb[3 * r + a] + c[a];
+    for (int a = 0; a < 3; ++a) c[a] = B.rgb[B.rgb_stride * r + a] + c[a];
   }
   if (B.finalize) {
     if (B.exposure) {
@@ -124,7 +124,8 @@ __device__ __forceinline__ void write_rgb(const BatchDev& B, long long r,
 #pragma unroll
     for (int a = 0; a < 3; ++a) c[a] = fminf(1.0f, fmaxf(0.0f, c[a]));
   }
-  B.rgb[3 * r] = c[0]; B.rgb[3 * r + 1] = c[1]; B.rgb[3 * r + 2] = c[2];
+  float* o = B.rgb + B.rgb_stride * r;
+  o[0] = c[0]; o[1] = c[1]; o[2] = c[2];
 }
 
 __device__ __forceinline__ void finalize_slot(const BatchDev& B, Slot* s) {
@@ -423,8 +424,8 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
       // -- depth now, colour when the last row of this ray has been composited ---------------------
       if (lane == 0) {
         float dpt = __fdiv_rn(dep, R.nrm) * R.blend;                   // tensorBase.py:615
-        if (B.accumulate) dpt = B.depth[ray] + dpt;
-        B.depth[ray] = dpt;
+        if (B.accumulate) dpt = B.depth[B.depth_stride * ray] + dpt;
+        B.depth[B.depth_stride * ray] = dpt;
         slot->acc = acc;
         __threadfence_block();
         const int old = atomicSub(&slot->pending, 1);                  // drop the open token

@@ -307,17 +307,38 @@ class LocalTensorfs(torch.nn.Module):
     # ---------------------------------------------------------------------------------------------
     # the hot path (local_tensorfs.py:382-499)
     # ---------------------------------------------------------------------------------------------
-    def _exposure_for(self, view_ids, test_id):
-        """Per-view 3x3 exposure; held-out frames average their neighbours (:481-493)."""
-        stacked = torch.stack(list(self.exposure), dim=0)
+    def _exposure_for(self, ids, test_id, dev):
+        """Per-view 3x3 exposure [V,3,3]; held-out frames average their neighbours with the
+        reference's edge rules (:481-493).  `ids` is the host list of view ids."""
         if not test_id:
-            return stacked[view_ids]
-        stacked = stacked.clone().detach()
-        lo = torch.clamp(view_ids - 1, min=0)
-        lo[lo == view_ids] = 1
-        hi = torch.clamp(view_ids + 1, max=len(self.exposure) - 1)
-        hi[lo == view_ids] = len(self.exposure) - 2
-        return (stacked[lo] + stacked[hi]) / 2
+            mats = [self.exposure[i] for i in ids]
+        else:
+            n = len(self.exposure)
+            mats = []
+            for v in ids:
+                lo = max(v - 1, 0)
+                if lo == v:
+                    lo = 1
+                hi = min(v + 1, n - 1)
+                if lo == v:                     # the reference re-tests the rewritten lower index
+                    hi = n - 2
+                mats.append((self.exposure[lo].detach() + self.exposure[hi].detach()) / 2)
+        out = mats[0].detach()[None] if len(mats) == 1 else torch.stack([m.detach() for m in mats])
+        return out.to(dev, torch.float32).contiguous()
+
+    def _cached(self, slot, key, build):
+        """Small memo for tensors derived from parameters: rebuilt when the key (ids + parameter
+        versions) changes, so an eval loop does not relaunch the pose / intrinsics arithmetic."""
+        c = self.__dict__.setdefault("_memo", {})
+        hit = c.get(slot)
+        if hit is None or hit[0] != key:
+            hit = (key, build())
+            c[slot] = hit
+        return hit[1]
+
+    def _blend_host(self):
+        bw = self.blending_weights
+        return self._cached("bw_host", (id(bw), bw._version), lambda: bw.detach().cpu())
 
     def forward(self, ray_ids, view_ids, W, H, white_bg=True, is_train=True, cam2world=None,
                 world2rf=None, blending_weights=None, chunk=16384, test_id=False,
@@ -326,49 +347,66 @@ class LocalTensorfs(torch.nn.Module):
         _require_cuda(ray_ids, "ray_ids")
         dev = ray_ids.device
         n = ray_ids.shape[0]
-        n_views = view_ids.shape[0]
-        if n % n_views != 0:
+        ids = view_ids.tolist() if torch.is_tensor(view_ids) else [int(v) for v in view_ids]
+        n_views = len(ids)
+        if n_views == 0 or n % n_views != 0:
             raise ValueError("ray_ids must hold the same number of rays for every view")
-        i, j = ids2pixel(W, H, ray_ids)
-        ij = torch.stack([i, j], dim=-1)
+        n_fields = len(self.tensorfs)
 
-        if blending_weights is None:
-            blending_weights = self.blending_weights[view_ids].clone()
-        else:
-            blending_weights = blending_weights.to(dev, torch.float32).clone()
-        if cam2world is None:
-            cam2world = self.get_cam2world(view_ids)
-        if world2rf is None:
-            world2rf = self.world2rf
+        # -- which fields render, with which per-view weights (:403-418) ----------------------------
+        blend = None                                   # device [V, n_fields] or None (= weight 1)
         if is_train:                                   # one field trains at a time (:411-416)
-            blending_weights[:, -1] = 1
-            blending_weights[:, :-1] = 0
-            active = [len(self.tensorfs) - 1]
+            active = [n_fields - 1]
+        elif blending_weights is None:
+            rows = self._blend_host()[ids]
+            active = torch.nonzero(rows.sum(dim=0))[:, 0].tolist()
+            bw = self.blending_weights
+            blend = bw.detach()[ids[0]:ids[0] + 1] if n_views == 1 else bw.detach()[view_ids]
+            blend = blend.to(dev, torch.float32).contiguous()
         else:
-            active = torch.nonzero(blending_weights.sum(dim=0))[:, 0].tolist()
+            blend = blending_weights.detach().to(dev, torch.float32).contiguous()
+            active = torch.nonzero(blend.sum(dim=0))[:, 0].tolist()
         if len(active) == 0:
             print("****** No valid RF")
+            i, j = ids2pixel(W, H, ray_ids)
             ones = torch.ones_like(ray_ids).float()
-            return torch.ones([n, 3], device=dev), ones, torch.zeros(n, 3, device=dev), ij
+            return torch.ones([n, 3], device=dev), ones, torch.zeros(n, 3, device=dev), torch.stack([i, j], -1)
 
+        if world2rf is None:
+            world2rf = self.world2rf
         grads = [cam2world, self.init_focal, self.focal_offset, self.center_rel]
         for k in active:
             grads += list(self.tensorfs[k].parameters())
         self.tensorfs[active[0]]._check_no_autograd(*grads)
 
-        cam2world = cam2world.detach().to(dev, torch.float32).contiguous()
-        blend = blending_weights.detach().contiguous()
+        # -- cameras, intrinsics, exposure (memoised on parameter versions) ---------------------------
+        if cam2world is None:
+            key = (tuple(ids), tuple(self.r_c2w[i]._version for i in ids),
+                   tuple(self.t_c2w[i]._version for i in ids), str(dev))
+            cam2world = self._cached("c2w", key, lambda: self.get_cam2world(ids).detach()
+                                     .to(dev, torch.float32).contiguous())
+        else:
+            cam2world = cam2world.detach().to(dev, torch.float32).contiguous()
         fov360 = self.fov == 360
-        intr = torch.cat([self.focal(W).detach().reshape(1),
-                          self.center(W, H).detach().reshape(2)]).to(dev, torch.float32).contiguous()
-        ids = ray_ids.detach().to(torch.int64).contiguous()
+        key = (W, H, self.init_focal._version, self.focal_offset._version, self.center_rel._version, str(dev))
+        intr = self._cached("intr", key, lambda: torch.cat(
+            [self.focal(W).detach().reshape(1), self.center(W, H).detach().reshape(2)])
+            .to(dev, torch.float32).contiguous())
         exposure = None
         if self.lr_exposure_init > 0:
-            exposure = self._exposure_for(view_ids, test_id).detach().to(dev, torch.float32).contiguous()
+            key = (tuple(ids), bool(test_id), len(self.exposure),
+                   tuple(self.exposure[i]._version for i in set(
+                       ids + [max(v - 1, 0) for v in ids] + [min(v + 1, len(self.exposure) - 1) for v in ids]
+                       + ([1, len(self.exposure) - 2] if test_id else []))), str(dev))
+            exposure = self._cached("expo", key, lambda: self._exposure_for(ids, test_id, dev))
+        rays_i = ray_ids.detach()
+        if rays_i.dtype != torch.int64 or not rays_i.is_contiguous():
+            rays_i = rays_i.to(torch.int64).contiguous()
 
         rgbs = torch.empty(n, 3, dtype=torch.float32, device=dev)
         depth = torch.empty(n, dtype=torch.float32, device=dev)
         directions = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        ij = torch.empty(n, 2, dtype=torch.int64, device=dev)
 
         # train mode: the reference draws fresh jitter per chunk; eval has no randomness, so the
         # whole batch is one launch per field.  Chunks are kept on view boundaries (the kernel
@@ -379,6 +417,7 @@ class LocalTensorfs(torch.nn.Module):
             chunk = max(per_view, (budget // per_view) * per_view)
         else:
             chunk = n
+        lib = _lib.lib()
         with torch.cuda.device(dev):
             stream = _stream(dev)
             for lo in range(0, n, chunk):
@@ -389,20 +428,23 @@ class LocalTensorfs(torch.nn.Module):
                     if rf.basis_mat.weight.device != dev:
                         rf.to(dev)
                     z = rf.sample_table(is_train, -1, dev)
-                    fs, keep = rf._field_struct(z)
-                    prep = rf.prepare(fs)
-                    w2rf = world2rf[k].detach().to(dev, torch.float32).contiguous()
+                    fs, prep = rf.field_and_prepared(z)
+                    w2 = world2rf[k]
+                    w2rf = w2.detach() if (w2.device == dev and w2.dtype == torch.float32
+                                            and w2.is_contiguous()) else \
+                        w2.detach().to(dev, torch.float32).contiguous()
                     b = _lib.LrfBatch()
                     b.n_rays = hi - lo
-                    b.ray_ids = ids.data_ptr() + 8 * lo
+                    b.ray_ids = rays_i.data_ptr() + 8 * lo
                     b.W, b.H = int(W), int(H)
                     b.fov360 = int(fov360)
                     b.intrinsics = intr.data_ptr()
                     b.cam2world = cam2world.data_ptr() + 48 * v_lo
                     b.n_views = v_hi - v_lo
                     b.world2rf = w2rf.data_ptr()
-                    b.blend = blend.data_ptr() + 4 * (v_lo * blend.shape[1] + k)
-                    b.blend_stride = blend.shape[1]
+                    if blend is not None:
+                        b.blend = blend.data_ptr() + 4 * (v_lo * blend.shape[1] + k)
+                        b.blend_stride = blend.shape[1]
                     b.accumulate = int(pos > 0)
                     b.finalize = int(pos == len(active) - 1)
                     if exposure is not None:
@@ -413,8 +455,8 @@ class LocalTensorfs(torch.nn.Module):
                     o.rgb = rgbs.data_ptr() + 12 * lo
                     o.depth = depth.data_ptr() + 4 * lo
                     o.directions = directions.data_ptr() + 12 * lo
+                    o.ij = ij.data_ptr() + 16 * lo
                     if stats is not None:
                         o.stats = stats.data_ptr()
-                    _lib.check(_lib.lib().lrf_render(C.byref(fs), _ptr(prep), C.byref(b),
-                                                     C.byref(o), stream))
+                    _lib.check(lib.lrf_render(C.byref(fs), _ptr(prep), C.byref(b), C.byref(o), stream))
         return rgbs, depth, directions, ij

@@ -188,6 +188,8 @@ class TensorBase(torch.nn.Module):
         if self.alphaMask is not None:
             self.alphaMask = self.alphaMask.to(device)
         self._prepared = None
+        self.__dict__.pop("_prep_memo", None)
+        self.__dict__.pop("_fs_memo", None)
         return super().to(device)
 
     # -- the per-batch distance table (tensorBase.py:419-437) -------------------------------------
@@ -299,6 +301,34 @@ class TensorBase(torch.nn.Module):
             self.__dict__[slot] = cached
         return cached[1]
 
+    def field_and_prepared(self, z):
+        """(LrfField struct, prepared block) for this field, memoised: the ctypes struct is rebuilt
+        only when a tensor it points at is replaced, the prepared block only when the MLP / basis
+        weights change (data pointer or version counter) -- every optimiser step while training,
+        never inside an eval loop."""
+        rm = self.renderModule
+        mlp = (self.basis_mat.weight, rm.mlp[0].weight, rm.mlp[0].bias, rm.mlp[2].weight,
+               rm.mlp[2].bias, rm.mlp_view[0].weight, rm.mlp_view[0].bias)
+        grids = tuple(self.density_plane) + tuple(self.density_line) + tuple(self.app_plane) + \
+            tuple(self.app_line)
+        am = self.alphaMask
+        k_struct = (tuple(t.data_ptr() for t in grids + mlp), z.data_ptr(), z.numel(),
+                    None if am is None else (am.alpha_volume.data_ptr(), am.aabb._version),
+                    self.aabb._version, tuple(self._grid_host), float(self.density_shift),
+                    float(self.distance_scale), float(self.rayMarch_weight_thres), self.fea2denseAct)
+        memo = self.__dict__.get("_fs_memo")
+        if memo is None or memo[0] != k_struct:
+            fs, keep = self._field_struct(z)
+            memo = (k_struct, fs, keep)
+            self.__dict__["_fs_memo"] = memo
+        fs = memo[1]
+        k_prep = tuple((t.data_ptr(), t._version) for t in mlp)
+        pm = self.__dict__.get("_prep_memo")
+        if pm is None or pm[0] != k_prep or self._prepared is None:
+            self.prepare(fs)
+            self.__dict__["_prep_memo"] = (k_prep,)
+        return fs, self._prepared
+
     def prepare(self, field_struct):
         """(Re)builds the folded / re-laid-out MLP block the kernel stages into shared memory."""
         dev = self.basis_mat.weight.device
@@ -354,8 +384,7 @@ class TensorBase(torch.nn.Module):
         # tensorBase.py:633 -- the coin is only tossed when white_bg is False and is_train
         bg = bool(white_bg) or bool(is_train and torch.rand((1,)) < 0.5)
         with torch.cuda.device(dev):
-            fs, keep = self._field_struct(z)
-            prep = self.prepare(fs)
+            fs, prep = self.field_and_prepared(z)
             rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
             depth = torch.empty(n, dtype=torch.float32, device=dev)
             weights = torch.empty(n, z.numel(), dtype=torch.float32, device=dev) if return_weights else None

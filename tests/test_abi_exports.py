@@ -33,7 +33,7 @@ def test_version_and_prepared_size():
 
 def test_struct_sizes_match_c_layout():
     # natural-alignment layouts of the header structs (x86-64)
-    assert C.sizeof(_lib.LrfOutputs) == 5 * 8
+    assert C.sizeof(_lib.LrfOutputs) == 7 * 8
     assert C.sizeof(_lib.LrfBatch) == 120
     assert C.sizeof(_lib.LrfField) % 8 == 0
 
