@@ -231,8 +231,7 @@ def main():
     # ---- device-resident step: direct C-ABI launch --------------------------------------------------
     view = torch.tensor([0], device=dev)
     z = rf.sample_table(False, -1, dev)
-    fs, keep = rf._field_struct(z)
-    prep = rf.prepare(fs)
+    fs, prep = rf.field_and_prepared(z)
     S = z.numel()
     c2w = lt.get_cam2world(view).detach().contiguous()
     intr = torch.cat([lt.focal(IMG_W).detach().reshape(1), lt.center(IMG_W, IMG_H).detach().reshape(2)]).contiguous()
@@ -248,6 +247,8 @@ def main():
     b.blend = blend.data_ptr(); b.blend_stride = 1; b.exposure = expo.data_ptr()
     b.accumulate = 0; b.finalize = 1; b.white_bg = 1; b.floater_thresh = 0.0
     o.rgb, o.depth, o.stats = rgb.data_ptr(), depth.data_ptr(), stats.data_ptr()
+    if world > 1:
+        o.pix = pix.data_ptr()          # interleaved (r,g,b,depth): one all-gather, no repack kernels
     lib = _lib.lib()
     stream = _stream(dev)
 
@@ -256,7 +257,6 @@ def main():
         b.ray_ids = ids_dev.data_ptr() + 8 * BATCH * bi
         _lib.check(lib.lrf_render(C.byref(fs), _ptr(prep), C.byref(b), C.byref(o), stream))
         if world > 1:
-            pix[:, :3] = rgb; pix[:, 3] = depth
             dist.all_gather_into_tensor(gathered, pix)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -305,15 +305,16 @@ def main():
 
     # ---- e2e: public API, host buffers, every step ---------------------------------------------------
     ids_host = frame_ids().pin_memory()
-    out_host = torch.empty(BATCH, 4, pin_memory=True)
+    rgb_host = torch.empty(BATCH, 3, pin_memory=True)
+    depth_host = torch.empty(BATCH, pin_memory=True)
     e2e_steps = args.steps
     def e2e_step(i):
         bi = ((i * world + rank) * 37) % n_batches
         ids = ids_host[bi * BATCH:(bi + 1) * BATCH].to(dev, non_blocking=True)
         with torch.no_grad():
             r, d, _, _ = lt(ids, view, IMG_W, IMG_H, is_train=False, chunk=BATCH)
-        out_host[:, :3].copy_(r, non_blocking=True)
-        out_host[:, 3].copy_(d, non_blocking=True)
+        rgb_host.copy_(r, non_blocking=True)
+        depth_host.copy_(d, non_blocking=True)
         torch.cuda.synchronize()
     for i in range(args.warmup):
         e2e_step(i)
