@@ -81,6 +81,7 @@ def test_three_field_blend_is_linear():
     torch.manual_seed(0)
     lt = bench.build_scene("cpu", 300)
     for k in (1, 2):
+        lt.append_frame()                      # append_rf needs >= 2 frames to cross-fade over
         torch.manual_seed(k)
         lt.append_rf(1)
     lt = lt.to("cuda")
