@@ -142,6 +142,22 @@ int lrf_density_feature(const LrfField *field, const float *xyz_norm, int64_t M,
 int lrf_app_feature(const LrfField *field, const float *xyz_norm, int64_t M, float *out,
                     lrf_stream_t stream);
 
+/* ---- training path (first step): differentiable lookups ------------------
+ * The 72 plane x line products of compute_appfeature BEFORE basis_mat (tensoRF.py:174-194 order):
+ * xyz_norm [M][3] -> out [M][3*n_acomp]. */
+int lrf_app_products(const LrfField *field, const float *xyz_norm, int64_t M, float *out,
+                     lrf_stream_t stream);
+/* Backward of lrf_density_feature (autograd of F.grid_sample x6 + product-sum, tensoRF.py:112-151):
+ * grad_out [M]; d_plane[i] / d_line[i] have the layout of the parameters and are ACCUMULATED into
+ * (atomic adds; zero them first); d_xyz [M][3] is overwritten (may be NULL). */
+int lrf_density_feature_backward(const LrfField *field, const float *xyz_norm,
+                                 const float *grad_out, int64_t M, float *const d_plane[3],
+                                 float *const d_line[3], float *d_xyz, lrf_stream_t stream);
+/* Backward of lrf_app_products: grad_out [M][3*n_acomp]; same conventions. */
+int lrf_app_products_backward(const LrfField *field, const float *xyz_norm, const float *grad_out,
+                              int64_t M, float *const d_plane[3], float *const d_line[3],
+                              float *d_xyz, lrf_stream_t stream);
+
 /* [C][H][W] (contiguous NCHW parameter of the reference) -> [H][W][C] */
 int lrf_repack_nchw_to_nhwc(const float *src, float *dst, int32_t C, int32_t H, int32_t W,
                             lrf_stream_t stream);

@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_CSRC, "liblrf_b200.so")
-SOURCES = ["lrf_render.cu", "lrf_aux.cu", "lrf_abi.cu"]
+SOURCES = ["lrf_render.cu", "lrf_aux.cu", "lrf_grad.cu", "lrf_abi.cu"]
 HEADERS = ["lrf_common.cuh", "lrf_device.cuh", os.path.join("..", "..", "include", "localrf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -65,7 +65,8 @@ class LrfOutputs(C.Structure):
 
 
 EXPORTS = ["lrf_version", "lrf_last_error", "lrf_prepared_bytes", "lrf_field_prepare",
-           "lrf_render", "lrf_mlp_forward", "lrf_density_feature", "lrf_app_feature", "lrf_repack_nchw_to_nhwc",
+           "lrf_render", "lrf_mlp_forward", "lrf_app_products", "lrf_density_feature_backward",
+           "lrf_app_products_backward", "lrf_density_feature", "lrf_app_feature", "lrf_repack_nchw_to_nhwc",
            "lrf_launch_info"]
 
 
@@ -117,6 +118,9 @@ def lib():
     L.lrf_mlp_forward.argtypes = [_vp, _vp, _vp, C.c_int64, _vp, _vp]
     L.lrf_density_feature.argtypes = [C.POINTER(LrfField), _vp, C.c_int64, _vp, _vp]
     L.lrf_app_feature.argtypes = [C.POINTER(LrfField), _vp, C.c_int64, _vp, _vp]
+    L.lrf_app_products.argtypes = [C.POINTER(LrfField), _vp, C.c_int64, _vp, _vp]
+    for name in ("lrf_density_feature_backward", "lrf_app_products_backward"):
+        getattr(L, name).argtypes = [C.POINTER(LrfField), _vp, _vp, C.c_int64, _vp * 3, _vp * 3, _vp, _vp]
     L.lrf_repack_nchw_to_nhwc.argtypes = [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]
     L.lrf_launch_info.argtypes = [C.POINTER(C.c_int32)] * 3
     for name in EXPORTS:

@@ -22,6 +22,14 @@ cudaError_t launch_density_feature(const FieldDev& F, const float* xyz, long lon
 cudaError_t launch_app_feature(const FieldDev& F, const float* basis, const float* xyz,
                                long long M, float* out, cudaStream_t stream);
 cudaError_t launch_repack(const float* src, float* dst, int C, long long HW, cudaStream_t stream);
+cudaError_t launch_app_products(const FieldDev& F, const float* xyz, long long M, float* out,
+                                cudaStream_t stream);
+cudaError_t launch_density_backward(const FieldDev& F, float* const* d_plane, float* const* d_line,
+                                    const float* xyz, const float* gout, long long M, float* dxyz,
+                                    cudaStream_t stream);
+cudaError_t launch_app_products_backward(const FieldDev& F, float* const* d_plane,
+                                         float* const* d_line, const float* xyz, const float* gout,
+                                         long long M, float* dxyz, cudaStream_t stream);
 }  // namespace lrf
 
 namespace {
@@ -241,6 +249,52 @@ int lrf_app_feature(const LrfField* f, const float* xyz, int64_t M, float* out,
   if (M < 0 || (M > 0 && (!xyz || !out))) return fail(LRF_ERR_INVALID, "bad xyz/out/M");
   cudaError_t e = lrf::launch_app_feature(F, f->basis, xyz, M, out, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "app_feature_kernel");
+  return LRF_OK;
+}
+
+int lrf_app_products(const LrfField* f, const float* xyz, int64_t M, float* out,
+                     lrf_stream_t stream) {
+  lrf::FieldDev F;
+  int rc = make_field(f, false, false, nullptr, F);
+  if (rc != LRF_OK) return rc;
+  if (M < 0 || (M > 0 && (!xyz || !out))) return fail(LRF_ERR_INVALID, "bad xyz/out/M");
+  cudaError_t e = lrf::launch_app_products(F, xyz, M, out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "app_products_kernel");
+  return LRF_OK;
+}
+
+static int check_grads(float* const d_plane[3], float* const d_line[3]) {
+  if (!d_plane || !d_line) return fail(LRF_ERR_INVALID, "gradient pointer arrays are NULL");
+  for (int i = 0; i < 3; ++i)
+    if (!d_plane[i] || !d_line[i]) return fail(LRF_ERR_INVALID, "gradient buffer is NULL");
+  return LRF_OK;
+}
+
+int lrf_density_feature_backward(const LrfField* f, const float* xyz, const float* gout, int64_t M,
+                                 float* const d_plane[3], float* const d_line[3], float* d_xyz,
+                                 lrf_stream_t stream) {
+  lrf::FieldDev F;
+  int rc = make_field(f, false, false, nullptr, F);
+  if (rc != LRF_OK) return rc;
+  if ((rc = check_grads(d_plane, d_line)) != LRF_OK) return rc;
+  if (M < 0 || (M > 0 && (!xyz || !gout))) return fail(LRF_ERR_INVALID, "bad xyz/grad_out/M");
+  cudaError_t e = lrf::launch_density_backward(F, d_plane, d_line, xyz, gout, M, d_xyz,
+                                               (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "density_backward_kernel");
+  return LRF_OK;
+}
+
+int lrf_app_products_backward(const LrfField* f, const float* xyz, const float* gout, int64_t M,
+                              float* const d_plane[3], float* const d_line[3], float* d_xyz,
+                              lrf_stream_t stream) {
+  lrf::FieldDev F;
+  int rc = make_field(f, false, false, nullptr, F);
+  if (rc != LRF_OK) return rc;
+  if ((rc = check_grads(d_plane, d_line)) != LRF_OK) return rc;
+  if (M < 0 || (M > 0 && (!xyz || !gout))) return fail(LRF_ERR_INVALID, "bad xyz/grad_out/M");
+  cudaError_t e = lrf::launch_app_products_backward(F, d_plane, d_line, xyz, gout, M, d_xyz,
+                                                    (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "app_products_backward_kernel");
   return LRF_OK;
 }
 

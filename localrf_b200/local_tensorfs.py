@@ -326,6 +326,58 @@ class LocalTensorfs(torch.nn.Module):
         out = mats[0].detach()[None] if len(mats) == 1 else torch.stack([m.detach() for m in mats])
         return out.to(dev, torch.float32).contiguous()
 
+    def _forward_autograd(self, ray_ids, view_ids, ids, W, H, white_bg, is_train, cam2world,
+                          world2rf, blend, active, chunk, test_id, floater_thresh):
+        """Training path (local_tensorfs.py:397-499 with autograd): rays are generated with torch
+        ops so gradients reach poses and intrinsics, each active field renders through
+        TensorBase._forward_autograd, blend / exposure / clamp are torch ops."""
+        from .ray_utils import get_ray_directions_360, get_ray_directions_lean, get_rays_lean
+        dev = ray_ids.device
+        n, n_views = ray_ids.shape[0], len(ids)
+        i, j = ids2pixel(W, H, ray_ids)
+        ij = torch.stack([i, j], dim=-1)
+        if self.fov == 360:
+            directions = get_ray_directions_360(i, j, W, H)
+        else:
+            directions = get_ray_directions_lean(i, j, self.focal(W), self.center(W, H))
+        if cam2world is None:
+            cam2world = self.get_cam2world(ids)
+        per_view = n // n_views
+        rgbs = torch.zeros_like(directions)
+        depth_maps = torch.zeros_like(directions[..., 0])
+        budget = max(chunk // len(active), 1)
+        step = n if n <= budget else max(per_view, (budget // per_view) * per_view)
+        outs_rgb, outs_depth = [], []
+        for lo in range(0, n, step):
+            hi = min(lo + step, n)
+            rgb_c = torch.zeros(hi - lo, 3, device=dev)
+            depth_c = torch.zeros(hi - lo, device=dev)
+            for k in active:
+                cam2rf = cam2world.clone()
+                cam2rf[:, :3, 3] = cam2rf[:, :3, 3] + world2rf[k]
+                cam2rf = cam2rf.repeat_interleave(per_view, dim=0)[lo:hi]
+                rays_o, rays_d = get_rays_lean(directions[lo:hi], cam2rf)
+                rgb_k, depth_k = self.tensorfs[k](torch.cat([rays_o, rays_d], -1), is_train=is_train,
+                                                  white_bg=white_bg, N_samples=-1,
+                                                  refine=self.is_refining,
+                                                  floater_thresh=floater_thresh)
+                if blend is None:
+                    w = 1.0
+                    rgb_c, depth_c = rgb_c + rgb_k, depth_c + depth_k
+                else:
+                    w = blend.repeat_interleave(per_view, dim=0)[lo:hi, k]
+                    rgb_c, depth_c = rgb_c + rgb_k * w[..., None], depth_c + depth_k * w
+            outs_rgb.append(rgb_c); outs_depth.append(depth_c)
+        rgbs = torch.cat(outs_rgb); depth_maps = torch.cat(outs_depth)
+        if self.lr_exposure_init > 0:
+            if test_id:
+                exposure = self._exposure_for(ids, True, dev)
+            else:
+                exposure = torch.stack([self.exposure[v] for v in ids], dim=0)
+            exposure = exposure.repeat_interleave(per_view, dim=0)
+            rgbs = torch.bmm(exposure, rgbs[..., None])[..., 0]
+        return rgbs.clamp(0, 1), depth_maps, directions, ij
+
     def _cached(self, slot, key, build):
         """Small memo for tensors derived from parameters: rebuilt when the key (ids + parameter
         versions) changes, so an eval loop does not relaunch the pose / intrinsics arithmetic."""
@@ -374,10 +426,17 @@ class LocalTensorfs(torch.nn.Module):
 
         if world2rf is None:
             world2rf = self.world2rf
-        grads = [cam2world, self.init_focal, self.focal_offset, self.center_rel]
-        for k in active:
-            grads += list(self.tensorfs[k].parameters())
-        self.tensorfs[active[0]]._check_no_autograd(*grads)
+        if torch.is_grad_enabled():
+            tracked = [self.init_focal, self.focal_offset, self.center_rel]
+            tracked += [cam2world] if cam2world is not None else \
+                [self.r_c2w[i] for i in ids] + [self.t_c2w[i] for i in ids]
+            tracked += [self.exposure[i] for i in ids] if self.lr_exposure_init > 0 else []
+            for k in active:
+                tracked += list(self.tensorfs[k].parameters())
+            if any(t is not None and t.requires_grad for t in tracked):
+                return self._forward_autograd(ray_ids, view_ids, ids, W, H, white_bg, is_train,
+                                              cam2world, world2rf, blend, active, chunk, test_id,
+                                              floater_thresh)
 
         # -- cameras, intrinsics, exposure (memoised on parameter versions) ---------------------------
         if cam2world is None:

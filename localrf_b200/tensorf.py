@@ -49,6 +49,42 @@ def _require_cuda(t, what):
             "(there is no CPU fallback)")
 
 
+class _VMLookup(torch.autograd.Function):
+    """Differentiable VM lookups of the training path: forward and backward are CUDA kernels behind
+    the C ABI (lrf_density_feature / lrf_app_products and their *_backward); gradients reach the
+    channel-last planes and lines by atomic adds and the sample coordinates by the bilinear
+    derivative (zero where grid_sample's border padding clips)."""
+
+    @staticmethod
+    def forward(ctx, module, kind, xyz, *grids):
+        ctx.module, ctx.kind = module, kind
+        xyz = xyz.detach().reshape(-1, 3).to(torch.float32).contiguous()
+        ctx.save_for_backward(xyz)
+        if kind == "density":
+            return module._feature_call_raw(xyz, "lrf_density_feature", 1)
+        return module._feature_call_raw(xyz, "lrf_app_products", 3 * module.app_n_comp[0])
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (xyz,) = ctx.saved_tensors
+        m, dev = ctx.module, xyz.device
+        planes, lines = (m.density_plane, m.density_line) if ctx.kind == "density" else \
+            (m.app_plane, m.app_line)
+        d_planes = [torch.zeros_like(p, memory_format=torch.channels_last) for p in planes]
+        d_lines = [torch.zeros_like(l, memory_format=torch.channels_last) for l in lines]
+        d_xyz = torch.empty_like(xyz) if ctx.needs_input_grad[2] else None
+        g = grad_out.detach().to(torch.float32).contiguous()
+        fn = getattr(_lib.lib(), "lrf_density_feature_backward" if ctx.kind == "density"
+                     else "lrf_app_products_backward")
+        with torch.cuda.device(dev):
+            fs, keep = m._field_struct(None, need_mlp=False)
+            pp = (C.c_void_p * 3)(*[t.data_ptr() for t in d_planes])
+            lp = (C.c_void_p * 3)(*[t.data_ptr() for t in d_lines])
+            _lib.check(fn(C.byref(fs), _ptr(xyz), _ptr(g), xyz.shape[0], pp, lp, _ptr(d_xyz),
+                          _stream(dev)))
+        return (None, None, d_xyz, *d_planes, *d_lines)
+
+
 class AlphaGridMask(torch.nn.Module):
     """models/tensorBase.py:38-62 -- binary occupancy volume, trilinearly sampled."""
 
@@ -370,7 +406,9 @@ class TensorBase(torch.nn.Module):
         distance table (parity tests feed the reference's own jittered table).
         """
         _require_cuda(rays_chunk, "rays_chunk")
-        self._check_no_autograd(rays_chunk, *self.parameters())
+        if self._wants_grad(rays_chunk, *self.parameters()):
+            return self._forward_autograd(rays_chunk, white_bg, is_train, N_samples, refine,
+                                          floater_thresh, return_weights, z_vals)
         dev = rays_chunk.device
         rays = rays_chunk.detach()
         if rays.dtype != torch.float32 or rays.dim() != 2 or rays.shape[1] < 6:
@@ -404,6 +442,61 @@ class TensorBase(torch.nn.Module):
                                              _stream(dev)))
         self.last_weights = weights
         return rgb, depth
+
+    def _forward_autograd(self, rays_chunk, white_bg, is_train, N_samples, refine, floater_thresh,
+                          return_weights, z_vals):
+        """The training path (autograd): the same algorithm as the fused kernel, composed from the
+        two differentiable CUDA lookups (`_VMLookup`: density feature, appearance products) and
+        torch ops for the cheap per-sample arithmetic and the dense MLP.  Gradients reach planes,
+        lines, basis, MLP and the rays (hence poses / intrinsics).  tensorBase.py:567-636."""
+        from .ray_utils import contract
+        dev = rays_chunk.device
+        rays_o, d = rays_chunk[:, :3], rays_chunk[:, 3:6]
+        norm = torch.norm(d, dim=-1, keepdim=True)
+        viewdirs = d / norm
+        z = self.sample_table(is_train, N_samples, dev) if z_vals is None else \
+            z_vals.detach().to(dev, torch.float32).reshape(-1)
+        z = z[None]                                                     # [1,S] like the reference
+        xyz = contract(rays_o[:, None, :] + viewdirs[:, None, :] * z[..., None])
+        n, S = xyz.shape[0], z.shape[1]
+        dists = torch.cat([z[:, 1:] - z[:, :-1], torch.zeros_like(z[:, :1])], dim=-1)
+        valid = torch.ones(n, S, dtype=torch.bool, device=dev)
+        if self.alphaMask is not None:
+            with torch.no_grad():
+                valid &= (self.alphaMask.sample_alpha(xyz.reshape(-1, 3)) > 0).view(n, S)
+        valid[:, -1] = False
+        xyzn = self.normalize_coord(xyz)
+        sigma = torch.zeros(n, S, device=dev)
+        if valid.any():
+            sigma = sigma.masked_scatter(valid, self.feature2density(
+                self.compute_densityfeature(xyzn[valid])))
+        alpha = 1.0 - torch.exp(-sigma * dists * self.distance_scale)
+
+        def weights_of(a):
+            a = torch.cat([a[:, :-1], torch.ones_like(a[:, :1])], dim=-1)      # alpha[:, -1] = 1
+            T = torch.cumprod(torch.cat([torch.ones_like(a[:, :1]), 1.0 - a + 1e-10], -1), -1)
+            return a * T[:, :-1]
+
+        weight = weights_of(alpha)
+        acc_map = weight.sum(-1)
+        depth_map = (weight * z).sum(-1) / norm[..., 0]
+        if floater_thresh > 0:
+            ks = torch.arange(S, device=dev)[None]
+            idx_map = (weight * ks).sum(-1, keepdim=True)
+            alpha = torch.where(ks < idx_map * floater_thresh, torch.zeros_like(alpha), alpha)
+            weight = weights_of(alpha)
+        app_mask = weight > self.rayMarch_weight_thres
+        rgb = torch.zeros(n, S, 3, device=dev)
+        if app_mask.any():
+            feats = self.compute_appfeature(xyzn[app_mask])
+            vd = viewdirs[:, None, :].expand(n, S, 3)[app_mask].clone().detach()
+            rgb = rgb.masked_scatter(app_mask[..., None].expand(n, S, 3),
+                                     self.renderModule(None, vd, feats, refine))
+        rgb_map = (weight[..., None] * rgb).sum(-2)
+        if white_bg or (is_train and torch.rand((1,)) < 0.5):
+            rgb_map = rgb_map + (1.0 - acc_map[..., None])
+        self.last_weights = weight.detach() if return_weights else None
+        return rgb_map, depth_map
 
     # -- off-path methods of the reference (host bookkeeping, stock torch) ------------------------
     def compute_alpha(self, xyz_locs, length=1):
@@ -475,9 +568,8 @@ class TensorVMSplit(TensorBase):
         return groups
 
     # -- feature lookups through the C ABI ---------------------------------------------------------
-    def _feature_call(self, xyz_sampled, fn_name, width):
+    def _feature_call_raw(self, xyz_sampled, fn_name, width):
         _require_cuda(xyz_sampled, "xyz_sampled")
-        self._check_no_autograd(xyz_sampled, *self.density_plane, *self.app_plane)
         dev = xyz_sampled.device
         xyz = xyz_sampled.detach().reshape(-1, 3).to(torch.float32).contiguous()
         m = xyz.shape[0]
@@ -488,13 +580,23 @@ class TensorVMSplit(TensorBase):
             _lib.check(fn(C.byref(fs), _ptr(xyz), m, _ptr(out), _stream(dev)))
         return out
 
+    @staticmethod
+    def _wants_grad(*tensors):
+        return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+
     def compute_densityfeature(self, xyz_sampled):
-        """tensoRF.py:112-151: [M,3] normalised coords -> [M]."""
-        return self._feature_call(xyz_sampled, "lrf_density_feature", 1)
+        """tensoRF.py:112-151: [M,3] normalised coords -> [M] (differentiable)."""
+        grids = list(self.density_plane) + list(self.density_line)
+        if self._wants_grad(xyz_sampled, *grids):
+            return _VMLookup.apply(self, "density", xyz_sampled, *grids)
+        return self._feature_call_raw(xyz_sampled, "lrf_density_feature", 1)
 
     def compute_appfeature(self, xyz_sampled):
-        """tensoRF.py:153-196: [M,3] normalised coords -> [M, app_dim]."""
-        return self._feature_call(xyz_sampled, "lrf_app_feature", self.app_dim)
+        """tensoRF.py:153-196: [M,3] normalised coords -> [M, app_dim] (differentiable)."""
+        grids = list(self.app_plane) + list(self.app_line)
+        if self._wants_grad(xyz_sampled, self.basis_mat.weight, *grids):
+            return self.basis_mat(_VMLookup.apply(self, "app", xyz_sampled, *grids))
+        return self._feature_call_raw(xyz_sampled, "lrf_app_feature", self.app_dim)
 
     # -- regularisers (tensoRF.py:66-110), stock torch ---------------------------------------------
     def vectorDiffs(self, vector_comps):

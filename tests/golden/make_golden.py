@@ -285,9 +285,64 @@ def gen_local():
         save(name, **arrays)
 
 
+# ---- G7: gradients of the reference (autograd) -- field level and scene level
+def gen_grads():
+    m = make_field([20, 24, 28], 40)
+    rays = rays_cfg1(64, seed=41).requires_grad_(True)
+    g = torch.Generator().manual_seed(42)
+    c_rgb = torch.randn(64, 3, generator=g)
+    c_depth = 0.1 * torch.randn(64, generator=g)
+    arrays = field_to_dict(m)
+    arrays["rays"] = rays.detach().numpy()
+    arrays["c_rgb"] = c_rgb.numpy(); arrays["c_depth"] = c_depth.numpy()
+    _captured.clear()
+    torch.manual_seed(43)
+    rgb, depth = m(rays, is_train=True)
+    loss = (rgb * c_rgb).sum() + (depth * c_depth).sum()
+    loss.backward()
+    arrays["z"] = _captured["z_list"][-1].numpy()
+    arrays["out.rgb"] = rgb.detach().numpy(); arrays["out.depth"] = depth.detach().numpy()
+    arrays["grad.rays"] = rays.grad.numpy()
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            arrays["grad." + k] = p.grad.numpy()
+    save("grads_field", **arrays)
+
+    lt = make_local(85.6, [24, 28, 20], n_frames=4, seed=20)
+    quiet(lt.append_rf, 2); quiet(lt.append_frame); quiet(lt.append_rf, 1); quiet(lt.append_frame)
+    with torch.no_grad():
+        gg = torch.Generator().manual_seed(21)
+        for i in range(len(lt.r_c2w)):
+            lt.r_c2w[i].add_(0.05 * torch.randn(3, 2, generator=gg))
+            lt.t_c2w[i].add_(0.2 * torch.randn(3, generator=gg))
+            lt.exposure[i].add_(0.05 * torch.randn(3, 3, generator=gg))
+        lt.world2rf[2].copy_(torch.tensor([-0.6, 0.1, 0.0]))
+    arrays = local_to_dict(lt)
+    W, H = 24, 20
+    gg = torch.Generator().manual_seed(22)
+    tv = torch.tensor([1, 4, 5, 2])
+    px = torch.randint(0, W * H, (4, 24), generator=gg)
+    tid = (px + tv[:, None] * W * H).reshape(-1)
+    c_rgb = torch.randn(96, 3, generator=gg); c_depth = 0.1 * torch.randn(96, generator=gg)
+    arrays.update({"ray_ids": tid.numpy(), "view_ids": tv.numpy(), "W": np.array(W), "H": np.array(H),
+                   "c_rgb": c_rgb.numpy(), "c_depth": c_depth.numpy()})
+    _captured.clear()
+    torch.manual_seed(44)
+    rgb, depth, dirs, ij = quiet(lt, tid, tv, W, H, is_train=True)
+    loss = (rgb * c_rgb).sum() + (depth * c_depth).sum()
+    loss.backward()
+    arrays["z"] = _captured["z_list"][-1].numpy()
+    arrays["out.rgb"] = rgb.detach().numpy(); arrays["out.depth"] = depth.detach().numpy()
+    for k, p in lt.named_parameters():
+        if p.grad is not None and float(p.grad.abs().sum()) > 0:
+            arrays["grad." + k] = p.grad.numpy()
+    save("grads_local", **arrays)
+
+
 if __name__ == "__main__":
     gen_cfg1()
     gen_aniso()
     gen_opaque()
     gen_alphamask()
     gen_local()
+    gen_grads()
