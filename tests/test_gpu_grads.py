@@ -114,3 +114,36 @@ def test_eval_path_still_fused_under_no_grad(monkeypatch):
     with torch.no_grad():
         m(torch.from_numpy(g["rays"]).cuda())
     assert not called
+
+
+def test_optimizer_step_like_train_py():
+    """The reference's training-loop shape (train.py:349-437): sample -> forward -> L1 loss ->
+    LocalTensorfs.optimizer_step (backward + Adam on field, poses, exposure); the loss goes down."""
+    import bench
+    import localrf_b200 as L
+    torch.manual_seed(0)
+    aabb = 2 * torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+    lt = L.LocalTensorfs(camera_prior=None, fov=85.6, n_init_frames=4, n_overlap=30, WH=(64, 48),
+                         n_iters_per_frame=600, n_iters_reg=100, lr_R_init=5e-3, lr_t_init=5e-4,
+                         lr_i_init=0, lr_exposure_init=1e-3, rf_lr_init=2e-2, rf_lr_basis=1e-3,
+                         lr_decay_target_ratio=0.1, N_voxel_list={}, update_AlphaMask_list=[],
+                         lr_upsample_reset=True, device="cuda", aabb=aabb.cuda(), gridSize=[48, 48, 48],
+                         **bench.field_kwargs()).cuda()
+    lt.is_refining = True
+    g = torch.Generator().manual_seed(1)
+    views = torch.tensor([0, 1, 2, 3], device="cuda")
+    px = torch.randint(0, 64 * 48, (4, 256), generator=g)
+    ids = (px + torch.arange(4)[:, None] * 64 * 48).reshape(-1).cuda()
+    target = torch.full((1024, 3), 0.25, device="cuda")
+    before = lt.tensorfs[-1].density_plane[0].detach().clone()
+    pose_before = lt.t_c2w[1].detach().clone()
+    losses = []
+    for it in range(12):
+        rgb, depth, dirs, ij = lt(ids, views, 64, 48, is_train=True)
+        loss = (rgb - target).abs().mean()
+        lt.optimizer_step(loss, optimize_poses=True)
+        losses.append(float(loss))
+    assert losses[-1] < losses[0] * 0.9, losses
+    assert not torch.equal(before, lt.tensorfs[-1].density_plane[0].detach())
+    assert not torch.equal(pose_before, lt.t_c2w[1].detach())
+    assert lt.tensorfs[-1].density_plane[0].is_contiguous(memory_format=torch.channels_last)
