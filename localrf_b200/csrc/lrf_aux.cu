@@ -277,12 +277,15 @@ cudaError_t launch_mlp(const float* prep, const float* feats, const float* viewd
                        float* rgb, int n_sms, cudaStream_t stream) {
   if (M == 0) return cudaSuccess;
   const size_t smem = (size_t)mlp_smem().total;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};   // per device
+  int dev = 0;
+  cudaError_t e0 = cudaGetDevice(&dev);
+  if (e0 != cudaSuccess) return e0;
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[dev] = true;
   }
   long long n_tiles = (M + TM - 1) / TM;
   int grid = (int)(n_tiles < n_sms ? n_tiles : n_sms);

@@ -602,14 +602,16 @@ cudaError_t launch_render(const FieldDev& F, const BatchDev& B, int n_sms, int m
   const int nprod = pick_nprod(F.S, floater, max_smem);
   if (nprod < 1) return cudaErrorInvalidConfiguration;
   const size_t smem = (size_t)smem_v3(F.S, floater, nprod).total;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+  static size_t configured[64] = {0};   // per device: the attribute belongs to the device's context
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && smem > configured[dev]) {
+    e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    configured[dev] = smem;
   }
-  cudaError_t e = cudaMemsetAsync(B.sched, 0, sizeof(unsigned long long), stream);
+  e = cudaMemsetAsync(B.sched, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
   // a CTA per SM, but never more CTAs than there are groups of 8 rays
   long long want = (B.n_rays + 7) / 8;
