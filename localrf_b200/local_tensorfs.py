@@ -378,19 +378,20 @@ class LocalTensorfs(torch.nn.Module):
             rgbs = torch.bmm(exposure, rgbs[..., None])[..., 0]
         return rgbs.clamp(0, 1), depth_maps, directions, ij
 
-    def _cached(self, slot, key, build):
-        """Small memo for tensors derived from parameters: rebuilt when the key (ids + parameter
-        versions) changes, so an eval loop does not relaunch the pose / intrinsics arithmetic."""
+    def _cached(self, slot, key, build, refs=()):
+        """Small memo for tensors derived from parameters: rebuilt when the key changes.  Keys are made
+        of ids + version counters of the source tensors; `refs` keeps those tensors alive while the
+        entry exists, so a freed tensor's id can never be reused by a different one."""
         c = self.__dict__.setdefault("_memo", {})
         hit = c.get(slot)
         if hit is None or hit[0] != key:
-            hit = (key, build())
+            hit = (key, build(), tuple(refs))
             c[slot] = hit
         return hit[1]
 
     def _blend_host(self):
         bw = self.blending_weights
-        return self._cached("bw_host", (id(bw), bw._version), lambda: bw.detach().cpu())
+        return self._cached("bw_host", (id(bw), bw._version), lambda: bw.detach().cpu(), refs=[bw])
 
     def forward(self, ray_ids, view_ids, W, H, white_bg=True, is_train=True, cam2world=None,
                 world2rf=None, blending_weights=None, chunk=16384, test_id=False,
@@ -399,6 +400,7 @@ class LocalTensorfs(torch.nn.Module):
         _require_cuda(ray_ids, "ray_ids")
         dev = ray_ids.device
         n = ray_ids.shape[0]
+        # (not memoised: a new tensor can reuse a freed tensor's id and storage)
         ids = view_ids.tolist() if torch.is_tensor(view_ids) else [int(v) for v in view_ids]
         n_views = len(ids)
         if n_views == 0 or n % n_views != 0:
@@ -440,24 +442,26 @@ class LocalTensorfs(torch.nn.Module):
 
         # -- cameras, intrinsics, exposure (memoised on parameter versions) ---------------------------
         if cam2world is None:
-            key = (tuple(ids), tuple(self.r_c2w[i]._version for i in ids),
-                   tuple(self.t_c2w[i]._version for i in ids), str(dev))
+            src = [self.r_c2w[i] for i in ids] + [self.t_c2w[i] for i in ids]
+            key = (tuple(ids), tuple((id(t), t._version) for t in src), str(dev))
             cam2world = self._cached("c2w", key, lambda: self.get_cam2world(ids).detach()
-                                     .to(dev, torch.float32).contiguous())
+                                     .to(dev, torch.float32).contiguous(), refs=src)
         else:
             cam2world = cam2world.detach().to(dev, torch.float32).contiguous()
         fov360 = self.fov == 360
-        key = (W, H, self.init_focal._version, self.focal_offset._version, self.center_rel._version, str(dev))
+        src = [self.init_focal, self.focal_offset, self.center_rel]
+        key = (W, H, self.W, tuple((id(t), t._version) for t in src), str(dev))
         intr = self._cached("intr", key, lambda: torch.cat(
             [self.focal(W).detach().reshape(1), self.center(W, H).detach().reshape(2)])
-            .to(dev, torch.float32).contiguous())
+            .to(dev, torch.float32).contiguous(), refs=src)
         exposure = None
         if self.lr_exposure_init > 0:
-            key = (tuple(ids), bool(test_id), len(self.exposure),
-                   tuple(self.exposure[i]._version for i in set(
-                       ids + [max(v - 1, 0) for v in ids] + [min(v + 1, len(self.exposure) - 1) for v in ids]
-                       + ([1, len(self.exposure) - 2] if test_id else []))), str(dev))
-            exposure = self._cached("expo", key, lambda: self._exposure_for(ids, test_id, dev))
+            n_e = len(self.exposure)
+            used = sorted(set(ids + ([max(v - 1, 0) for v in ids] + [min(v + 1, n_e - 1) for v in ids]
+                                     + [min(1, n_e - 1), max(n_e - 2, 0)] if test_id else [])))
+            src = [self.exposure[i] for i in used]
+            key = (tuple(ids), bool(test_id), n_e, tuple((id(t), t._version) for t in src), str(dev))
+            exposure = self._cached("expo", key, lambda: self._exposure_for(ids, test_id, dev), refs=src)
         rays_i = ray_ids.detach()
         if rays_i.dtype != torch.int64 or not rays_i.is_contiguous():
             rays_i = rays_i.to(torch.int64).contiguous()

@@ -333,7 +333,8 @@ class TensorBase(torch.nn.Module):
         key = (id(param), param._version, param.device)
         cached = self.__dict__.get(slot)
         if cached is None or cached[0] != key:
-            cached = (key, param.detach().reshape(-1).tolist())
+            # the entry keeps `param` alive, so its id cannot be recycled by another tensor
+            cached = (key, param.detach().reshape(-1).tolist(), param)
             self.__dict__[slot] = cached
         return cached[1]
 
@@ -355,14 +356,15 @@ class TensorBase(torch.nn.Module):
         memo = self.__dict__.get("_fs_memo")
         if memo is None or memo[0] != k_struct:
             fs, keep = self._field_struct(z)
-            memo = (k_struct, fs, keep)
+            # hold every tensor whose address the struct stores: no recycled pointers while cached
+            memo = (k_struct, fs, keep, grids + mlp + (z,) + (() if am is None else (am.alpha_volume,)))
             self.__dict__["_fs_memo"] = memo
         fs = memo[1]
         k_prep = tuple((t.data_ptr(), t._version) for t in mlp)
         pm = self.__dict__.get("_prep_memo")
         if pm is None or pm[0] != k_prep or self._prepared is None:
             self.prepare(fs)
-            self.__dict__["_prep_memo"] = (k_prep,)
+            self.__dict__["_prep_memo"] = (k_prep, mlp)
         return fs, self._prepared
 
     def prepare(self, field_struct):

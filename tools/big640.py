@@ -1,5 +1,5 @@
 import sys, time, torch, numpy as np
-sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
 from helpers import rel_err
 lt = bench.build_scene(torch.device("cuda"), 640)

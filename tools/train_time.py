@@ -1,5 +1,5 @@
 import sys, time, torch
-sys.path.insert(0, ".")
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 lt = bench.build_scene(torch.device("cuda"), 300)
 lt.is_refining = True
