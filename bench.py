@@ -321,7 +321,12 @@ def main():
     if world == 1:
         achieved = bytes_total / (kern_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the
+                    # committed `ncu --set full` capture (profiles/r1_v3_streaming.md): 4.08 MB + 0 B
+                    "traffic": 4.08e6, "traffic_unit": "bytes per launch (ncu, profiles/r1_v3_streaming.md)",
+                    "algorithmic_bytes_per_launch": bytes_total / args.steps,
+                    "peak_source": peak_src,
                     "kernel": "lrf::render_kernel",
                     "bytes_per_ray": bytes_total / (BATCH * args.steps),
                     "density_samples_per_ray": st[0] / (BATCH * args.steps),
