@@ -42,30 +42,23 @@ class LocalTensorfs(torch.nn.Module):
                  lr_decay_target_ratio, N_voxel_list, update_AlphaMask_list, camera_prior, device,
                  lr_upsample_reset, **tensorf_args):
         super().__init__()
-        self.fov = fov
-        self.n_init_frames = n_init_frames
-        self.n_overlap = n_overlap
+        # hyper-parameters, under the attribute names the reference's callers read
+        # (local_tensorfs.py:61-82); the *_per_frame_* copies feed the per-field schedule rescaling
         self.W, self.H = WH
-        self.n_iters_per_frame = n_iters_per_frame
-        self.n_iters_reg_per_frame = n_iters_reg
-        self.lr_R_init, self.lr_t_init = lr_R_init, lr_t_init
-        self.lr_i_init, self.lr_exposure_init = lr_i_init, lr_exposure_init
-        self.rf_lr_init, self.rf_lr_basis = rf_lr_init, rf_lr_basis
-        self.lr_decay_target_ratio = lr_decay_target_ratio
-        self.N_voxel_per_frame_list = N_voxel_list
-        self.update_AlphaMask_per_frame_list = update_AlphaMask_list
-        self.device = torch.device(device)
-        self.camera_prior = camera_prior
-        self.tensorf_args = tensorf_args
-        self.is_refining = False
-        self.lr_upsample_reset = lr_upsample_reset
-
-        self.lr_factor = 1
-        self.regularize = True
-        self.n_iters_reg = self.n_iters_reg_per_frame
-        self.n_iters = self.n_iters_per_frame
-        self.update_AlphaMask_list = update_AlphaMask_list
-        self.N_voxel_list = N_voxel_list
+        for name, value in dict(
+                fov=fov, n_init_frames=n_init_frames, n_overlap=n_overlap,
+                n_iters_per_frame=n_iters_per_frame, n_iters_reg_per_frame=n_iters_reg,
+                lr_R_init=lr_R_init, lr_t_init=lr_t_init, lr_i_init=lr_i_init,
+                lr_exposure_init=lr_exposure_init, rf_lr_init=rf_lr_init, rf_lr_basis=rf_lr_basis,
+                lr_decay_target_ratio=lr_decay_target_ratio, N_voxel_per_frame_list=N_voxel_list,
+                update_AlphaMask_per_frame_list=update_AlphaMask_list, camera_prior=camera_prior,
+                tensorf_args=tensorf_args, lr_upsample_reset=lr_upsample_reset,
+                device=torch.device(device)).items():
+            setattr(self, name, value)
+        # schedule state of the field being optimised (rescaled in optimizer_step at iteration 1)
+        self.is_refining, self.regularize, self.lr_factor = False, True, 1
+        self.n_iters, self.n_iters_reg = n_iters_per_frame, n_iters_reg
+        self.N_voxel_list, self.update_AlphaMask_list = N_voxel_list, update_AlphaMask_list
 
         # per-frame pose / exposure parameters, one optimiser each (local_tensorfs.py:85-92)
         self.r_c2w = torch.nn.ParameterList()
@@ -241,18 +234,16 @@ class LocalTensorfs(torch.nn.Module):
             t = torch.stack(list(self.t_c2w[starting_id:]), dim=0)
         return torch.cat([sixD_to_mtx(r), t[..., None]], dim=-1)
 
+    _CKPT_FIELDS = ("fov", "n_init_frames", "n_overlap", "n_iters_per_frame", "lr_R_init", "lr_t_init",
+                    "lr_i_init", "lr_exposure_init", "rf_lr_init", "rf_lr_basis",
+                    "lr_decay_target_ratio", "lr_upsample_reset")
+
     def get_kwargs(self):
-        kwargs = {
-            "camera_prior": None, "fov": self.fov, "n_init_frames": self.n_init_frames,
-            "n_overlap": self.n_overlap, "WH": (self.W, self.H),
-            "n_iters_per_frame": self.n_iters_per_frame, "n_iters_reg": self.n_iters_reg_per_frame,
-            "lr_R_init": self.lr_R_init, "lr_t_init": self.lr_t_init, "lr_i_init": self.lr_i_init,
-            "lr_exposure_init": self.lr_exposure_init, "rf_lr_init": self.rf_lr_init,
-            "rf_lr_basis": self.rf_lr_basis, "lr_decay_target_ratio": self.lr_decay_target_ratio,
-            "N_voxel_list": self.N_voxel_per_frame_list,
-            "update_AlphaMask_list": self.update_AlphaMask_per_frame_list,
-            "lr_upsample_reset": self.lr_upsample_reset,
-        }
+        """Constructor kwargs stored next to the state_dict in a checkpoint (:301-324)."""
+        kwargs = {name: getattr(self, name) for name in self._CKPT_FIELDS}
+        kwargs.update(camera_prior=None, WH=(self.W, self.H), n_iters_reg=self.n_iters_reg_per_frame,
+                      N_voxel_list=self.N_voxel_per_frame_list,
+                      update_AlphaMask_list=self.update_AlphaMask_per_frame_list)
         kwargs.update(self.tensorfs[0].get_kwargs())
         return kwargs
 
