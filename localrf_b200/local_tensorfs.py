@@ -319,9 +319,11 @@ class LocalTensorfs(torch.nn.Module):
 
     def _forward_autograd(self, ray_ids, view_ids, ids, W, H, white_bg, is_train, cam2world,
                           world2rf, blend, active, chunk, test_id, floater_thresh):
-        """Training path (local_tensorfs.py:397-499 with autograd): rays are generated with torch
-        ops so gradients reach poses and intrinsics, each active field renders through
-        TensorBase._forward_autograd, blend / exposure / clamp are torch ops."""
+        """Composed path (local_tensorfs.py:397-499 with torch ops around the CUDA lookups): rays are
+        generated with torch ops so gradients reach poses and intrinsics, each active field renders
+        through TensorBase.forward (composed when autograd records or the field uses positional
+        encodings), blend / exposure / clamp are torch ops.  Chunked like the reference, because
+        this path materialises per-sample tensors."""
         from .ray_utils import get_ray_directions_360, get_ray_directions_lean, get_rays_lean
         dev = ray_ids.device
         n, n_views = ray_ids.shape[0], len(ids)
@@ -426,10 +428,13 @@ class LocalTensorfs(torch.nn.Module):
             tracked += [self.exposure[i] for i in ids] if self.lr_exposure_init > 0 else []
             for k in active:
                 tracked += list(self.tensorfs[k].parameters())
-            if any(t is not None and t.requires_grad for t in tracked):
-                return self._forward_autograd(ray_ids, view_ids, ids, W, H, white_bg, is_train,
-                                              cam2world, world2rf, blend, active, chunk, test_id,
-                                              floater_thresh)
+            needs_composed = any(t is not None and t.requires_grad for t in tracked)
+        else:
+            needs_composed = False
+        if needs_composed or not all(self.tensorfs[k].fused_supported() for k in active):
+            return self._forward_autograd(ray_ids, view_ids, ids, W, H, white_bg, is_train,
+                                          cam2world, world2rf, blend, active, chunk, test_id,
+                                          floater_thresh)
 
         # -- cameras, intrinsics, exposure (memoised on parameter versions) ---------------------------
         if cam2world is None:

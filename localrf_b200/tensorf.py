@@ -408,7 +408,7 @@ class TensorBase(torch.nn.Module):
         distance table (parity tests feed the reference's own jittered table).
         """
         _require_cuda(rays_chunk, "rays_chunk")
-        if self._wants_grad(rays_chunk, *self.parameters()):
+        if self._wants_grad(rays_chunk, *self.parameters()) or not self.fused_supported():
             return self._forward_autograd(rays_chunk, white_bg, is_train, N_samples, refine,
                                           floater_thresh, return_weights, z_vals)
         dev = rays_chunk.device
@@ -445,12 +445,19 @@ class TensorBase(torch.nn.Module):
         self.last_weights = weights
         return rgb, depth
 
+    def fused_supported(self):
+        """Configurations the fused kernel covers (the reference defaults).  Anything else that is
+        valid for MLP_Fea_late_view -- positional encodings -- renders through the composed path
+        below (CUDA lookups + torch MLP), on the GPU, at the reference's semantics."""
+        return self.fea_pe == 0 and self.view_pe == 0 and self.app_dim == 27 and self.featureC == 128
+
     def _forward_autograd(self, rays_chunk, white_bg, is_train, N_samples, refine, floater_thresh,
                           return_weights, z_vals):
-        """The training path (autograd): the same algorithm as the fused kernel, composed from the
-        two differentiable CUDA lookups (`_VMLookup`: density feature, appearance products) and
-        torch ops for the cheap per-sample arithmetic and the dense MLP.  Gradients reach planes,
-        lines, basis, MLP and the rays (hence poses / intrinsics).  tensorBase.py:567-636."""
+        """The composed path: the same algorithm as the fused kernel, built from the two
+        differentiable CUDA lookups (`_VMLookup`: density feature, appearance products) and torch ops
+        for the cheap per-sample arithmetic and the dense MLP.  Used when autograd is recording
+        (training: gradients reach planes, lines, basis, MLP and the rays, hence poses and
+        intrinsics) and for configurations the fused kernel does not cover.  tensorBase.py:567-636."""
         from .ray_utils import contract
         dev = rays_chunk.device
         rays_o, d = rays_chunk[:, :3], rays_chunk[:, 3:6]
