@@ -142,7 +142,7 @@ def test_optimizer_step_like_train_py():
         rgb, depth, dirs, ij = lt(ids, views, 64, 48, is_train=True)
         loss = (rgb - target).abs().mean()
         lt.optimizer_step(loss, optimize_poses=True)
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[-1] < losses[0] * 0.9, losses
     assert not torch.equal(before, lt.tensorfs[-1].density_plane[0].detach())
     assert not torch.equal(pose_before, lt.t_c2w[1].detach())
