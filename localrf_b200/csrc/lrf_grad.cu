@@ -40,7 +40,14 @@ __global__ void app_products_kernel(const FieldDev F, const float* __restrict__ 
   }
 }
 
+// 16-byte vector reduction (red.global.add.v4.f32, sm_90+): one atomic per 4 components
+__device__ __forceinline__ void red4(float* p, float x, float y, float z, float w) {
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(x, y, z, w));
+}
+
 // backward of one plane/line pair with C components.  g(c) = dL/d(plane_c * line_c).
+// Components are contiguous in memory (channel-last), so parameters are read and their gradients
+// accumulated four at a time.
 template <int C, class G>
 __device__ __forceinline__ void vm_pair_backward(const int* g3, int i, const float* plane,
                                                  const float* line, float* d_plane, float* d_line,
@@ -55,26 +62,34 @@ __device__ __forceinline__ void vm_pair_backward(const int* g3, int i, const flo
   const size_t o10 = ((size_t)y1 * W + x0) * C, o11 = ((size_t)y1 * W + x1) * C;
   const size_t ol0 = (size_t)l0 * C, ol1 = (size_t)l1 * C;
   const float w00 = (1.0f - tx) * (1.0f - ty), w01 = tx * (1.0f - ty);
-  const float w10 = (1.0f - tx) * ty, w11 = tx * ty;
+  const float w10 = (1.0f - tx) * ty, w11 = tx * ty, u0 = 1.0f - tl;
   float gx = 0.0f, gy = 0.0f, gl = 0.0f;
-#pragma unroll 4
-  for (int c = 0; c < C; ++c) {
-    const float a = __ldg(plane + o00 + c), b = __ldg(plane + o01 + c);
-    const float cc = __ldg(plane + o10 + c), d = __ldg(plane + o11 + c);
-    const float u = __ldg(line + ol0 + c), v = __ldg(line + ol1 + c);
-    const float P = a * w00 + b * w01 + cc * w10 + d * w11;
-    const float Lc = u * (1.0f - tl) + v * tl;
-    const float gc = g(c);
-    const float dP = gc * Lc, dLc = gc * P;
-    atomicAdd(d_plane + o00 + c, dP * w00);
-    atomicAdd(d_plane + o01 + c, dP * w01);
-    atomicAdd(d_plane + o10 + c, dP * w10);
-    atomicAdd(d_plane + o11 + c, dP * w11);
-    atomicAdd(d_line + ol0 + c, dLc * (1.0f - tl));
-    atomicAdd(d_line + ol1 + c, dLc * tl);
-    gx += dP * ((b - a) * (1.0f - ty) + (d - cc) * ty);
-    gy += dP * ((cc - a) * (1.0f - tx) + (d - b) * tx);
-    gl += dLc * (v - u);
+#pragma unroll 2
+  for (int c = 0; c < C; c += 4) {
+    const float4 a = ldg4(plane + o00 + c), b = ldg4(plane + o01 + c);
+    const float4 cc = ldg4(plane + o10 + c), d = ldg4(plane + o11 + c);
+    const float4 u = ldg4(line + ol0 + c), v = ldg4(line + ol1 + c);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, dv[4] = {d.x, d.y, d.z, d.w};
+    const float uv[4] = {u.x, u.y, u.z, u.w}, vv[4] = {v.x, v.y, v.z, v.w};
+    float dP[4], dLc[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float P = av[e] * w00 + bv[e] * w01 + cv[e] * w10 + dv[e] * w11;
+      const float Lc = uv[e] * u0 + vv[e] * tl;
+      const float gc = g(c + e);
+      dP[e] = gc * Lc;
+      dLc[e] = gc * P;
+      gx += dP[e] * ((bv[e] - av[e]) * (1.0f - ty) + (dv[e] - cv[e]) * ty);
+      gy += dP[e] * ((cv[e] - av[e]) * (1.0f - tx) + (dv[e] - bv[e]) * tx);
+      gl += dLc[e] * (vv[e] - uv[e]);
+    }
+    red4(d_plane + o00 + c, dP[0] * w00, dP[1] * w00, dP[2] * w00, dP[3] * w00);
+    red4(d_plane + o01 + c, dP[0] * w01, dP[1] * w01, dP[2] * w01, dP[3] * w01);
+    red4(d_plane + o10 + c, dP[0] * w10, dP[1] * w10, dP[2] * w10, dP[3] * w10);
+    red4(d_plane + o11 + c, dP[0] * w11, dP[1] * w11, dP[2] * w11, dP[3] * w11);
+    red4(d_line + ol0 + c, dLc[0] * u0, dLc[1] * u0, dLc[2] * u0, dLc[3] * u0);
+    red4(d_line + ol1 + c, dLc[0] * tl, dLc[1] * tl, dLc[2] * tl, dLc[3] * tl);
   }
   dq[mat0(i)] += gx * dx;
   dq[mat1(i)] += gy * dy;
