@@ -44,6 +44,27 @@ FOV = 85.6
 FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print (NCCL's version banner, torchrun notices) goes to stderr; only the
+    ONE JSON line reaches the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def field_kwargs():
     return dict(density_n_comp=[8, 8, 8], appearance_n_comp=[24, 24, 24], app_dim=27,
                 shadingMode="MLP_Fea_late_view", near_far=[0.1, 1e3], density_shift=-5,
@@ -205,7 +226,7 @@ def run_reference(args):
         step(args.warmup + i)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "rays/sec at 300^3 VM grid, 4096-ray batch", "value": value,
         "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -215,7 +236,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": f"{n} rays per step, oracle/lrf_oracle.c, OpenMP {os.cpu_count()} threads"},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def main():
@@ -227,6 +248,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grid", type=int, default=GRID)
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.warmup < 3:
@@ -401,7 +423,7 @@ def main():
         "cpu_baseline": cpu,
         "frame_api": frame,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
