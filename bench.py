@@ -169,8 +169,11 @@ def oracle_field(lt):
     return orc.Field(fd)
 
 
-def oracle_batch(lt, field, ids, n_threads=0):
-    """One batch through the CPU oracle's LocalTensorfs.forward restatement."""
+def oracle_batch(lt, field, ids, n_threads=None):
+    """One batch through the CPU oracle's LocalTensorfs.forward restatement, on ALL host cores
+    (explicit thread count: torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    if n_threads is None:
+        n_threads = os.cpu_count() or 1
     from oracle import oracle as orc
     z = orc.sample_table(field.n_samples())
     focal = float(lt.focal(IMG_W).detach().cpu())
