@@ -20,17 +20,11 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FC >
                            ((uint32_t)(TM >> 4) << 24);
 constexpr float T_EPS = 1e-10f;  // early-termination transmittance (error bound)
 
-struct RaySm {
-  float o[3];
-  float vd[3];
-  float nrm;
-  float blend;
-  float rgb[3];
-  float depth;
-  float acc;
-  int count;
-  int offset;
-  int valid;
+struct RaySm {                     // one ray, as set up by setup_ray
+  float o[3];                      // origin in the field's frame
+  float vd[3];                     // normalised direction (tensorBase.py:578-580)
+  float nrm;                       // |d| before normalisation (depth is divided by it, :615)
+  float blend;                     // this field's blending weight for the ray's view
 };
 
 // ---- PTX helpers: mbarrier + TMA 1-D bulk copy ---------------------------------------------------
@@ -261,8 +255,6 @@ __device__ __forceinline__ void setup_ray(const BatchDev& B, long long r, RaySm&
 #pragma unroll
   for (int a = 0; a < 3; ++a) { R.o[a] = o[a]; R.vd[a] = __fdiv_rn(d[a], n); }
   R.blend = B.blend ? B.blend[view * B.blend_stride] : 1.0f;
-  R.rgb[0] = R.rgb[1] = R.rgb[2] = 0.0f;
-  R.depth = 0.0f; R.acc = 0.0f; R.count = 0; R.offset = 0; R.valid = 1;
 }
 
 // sample position in the field's normalised [-1,1]^3 grid coordinates (tensorBase.py:438-440,602)
@@ -380,22 +372,6 @@ __device__ __forceinline__ float warp_scan_mul(float v, int lane) {
   return v;
 }
 
-// weights of one ray from its alphas in shared memory: w[k] = alpha[k] * prod_{j<k}(1-alpha[j]+1e-10)
-// (alpha2weights, tensorBase.py:23-32).  Returns nothing; writes w_s.
-__device__ __forceinline__ void rescan_weights(const float* alpha_s, float* w_s, int S, int lane) {
-  float carry = 1.0f;
-  for (int k0 = 0; k0 < S; k0 += 32) {
-    int k = k0 + lane;
-    float a = (k < S) ? alpha_s[k] : 0.0f;
-    if (k == S - 1) a = 1.0f;
-    float f = (k < S) ? (1.0f - a) + 1e-10f : 1.0f;
-    float inc = warp_scan_mul(f, lane);
-    float exc = __shfl_up_sync(0xffffffffu, inc, 1);
-    if (lane == 0) exc = 1.0f;
-    if (k < S) w_s[k] = a * (carry * exc);
-    carry *= __shfl_sync(0xffffffffu, inc, 31);
-  }
-}
 
 
 }  // namespace lrf

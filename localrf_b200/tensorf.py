@@ -392,12 +392,6 @@ class TensorBase(torch.nn.Module):
                                                   _ptr(out), _stream(dev)))
         return out
 
-    def _check_no_autograd(self, *tensors):
-        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-            raise NotImplementedError(
-                "localrf_b200: the fused backward is not built yet (SURVEY.md §8f rank 1); call "
-                "the render path under torch.no_grad()")
-
     # -- the hot path ------------------------------------------------------------------------------
     def forward(self, rays_chunk, white_bg=True, is_train=False, N_samples=-1, refine=True,
                 floater_thresh=0, return_weights=False, stats=None, z_vals=None):
