@@ -413,6 +413,9 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "dtype_note": "fp32 storage and arithmetic; the two dense MLP layers run on tcgen05 as three bf16 "
+                      "products of hi/lo-split fp32 operands with fp32 TMEM accumulators (1e-7 of fp32 on rgb, "
+                      "tests/test_gpu_parity.py::test_tensor_core_mlp_vs_torch_fp32)",
         "config": {"workload": f"cfg2: TensorVMSplit {args.grid}^3 (reference ctor, seed 0, random init), "
                                "800x800 pinhole frame fov 85.6 identity pose, 4096-ray batches; "
                                "step = one batch, steps walk the frame's batches",
