@@ -443,3 +443,206 @@ void orc_local_forward(const OrcField *fields, int32_t n_fields, const float *co
   }
   free(rays); free(rgb_t); free(depth_t);
 }
+
+/* =================================================================================================
+ * Backward of TensorBase.forward (floater_thresh = 0, fea_pe = view_pe = 0): the analytic gradients
+ * torch autograd produces through tensorBase.py:567-636 / tensoRF.py:112-196.  Single-threaded,
+ * sample by sample (it is a checker, sized for the small golden fields).
+ * ================================================================================================= */
+
+/* grid_sample(align_corners=True, padding_mode="border") coordinate with its derivative
+ * (ATen clip_coordinates_set_grad: zero gradient when the un-normalised coordinate is clipped) */
+static inline void coord_grad(float c, int size, int *i0, int *i1, float *t, float *dcoord) {
+  float x = ((c + 1.0f) / 2.0f) * (float)(size - 1);
+  *dcoord = (x <= 0.0f || x >= (float)(size - 1)) ? 0.0f : 0.5f * (float)(size - 1);
+  x = fminf((float)(size - 1), fmaxf(x, 0.0f));
+  float fl = floorf(x);
+  *i0 = (int)fl;
+  *i1 = (*i0 + 1 <= size - 1) ? *i0 + 1 : size - 1;
+  *t = x - fl;
+}
+
+/* backward of sum_c bilinear(plane_c)(x,y) * linear(line_c)(l) weighted by g[c]; reference layouts
+ * plane [C][H][W], line [C][L]; accumulates into dplane / dline and dq[3] */
+static void vm_pair_backward(const int *grid, int i, int C, const float *plane, const float *line,
+                             float *dplane, float *dline, const float *q, const float *g, int g_stride,
+                             float *dq) {
+  int W = grid[MAT0[i]], H = grid[MAT1[i]], L = grid[VEC[i]];
+  int x0, x1, y0, y1, l0, l1;
+  float tx, ty, tl, dx, dy, dl;
+  coord_grad(q[MAT0[i]], W, &x0, &x1, &tx, &dx);
+  coord_grad(q[MAT1[i]], H, &y0, &y1, &ty, &dy);
+  coord_grad(q[VEC[i]], L, &l0, &l1, &tl, &dl);
+  float w00 = (1 - tx) * (1 - ty), w01 = tx * (1 - ty), w10 = (1 - tx) * ty, w11 = tx * ty;
+  float gx = 0, gy = 0, gl = 0;
+  for (int c = 0; c < C; ++c) {
+    const float *p = plane + (size_t)c * H * W;
+    float *dp = dplane + (size_t)c * H * W;
+    float a = p[(size_t)y0 * W + x0], b = p[(size_t)y0 * W + x1];
+    float cc = p[(size_t)y1 * W + x0], d = p[(size_t)y1 * W + x1];
+    float u = line[(size_t)c * L + l0], v = line[(size_t)c * L + l1];
+    float P = a * w00 + b * w01 + cc * w10 + d * w11, Lc = u * (1 - tl) + v * tl;
+    float gc = g[c * g_stride], dP = gc * Lc, dLc = gc * P;
+    dp[(size_t)y0 * W + x0] += dP * w00; dp[(size_t)y0 * W + x1] += dP * w01;
+    dp[(size_t)y1 * W + x0] += dP * w10; dp[(size_t)y1 * W + x1] += dP * w11;
+    dline[(size_t)c * L + l0] += dLc * (1 - tl); dline[(size_t)c * L + l1] += dLc * tl;
+    gx += dP * ((b - a) * (1 - ty) + (d - cc) * ty);
+    gy += dP * ((cc - a) * (1 - tx) + (d - b) * tx);
+    gl += dLc * (v - u);
+  }
+  dq[MAT0[i]] += gx * dx; dq[MAT1[i]] += gy * dy; dq[VEC[i]] += gl * dl;
+}
+
+/* d(contract(p))/dp applied to dpc (utils/ray_utils.py:9-12; amax routes the norm's gradient to the
+ * largest |component|) */
+static void contract_backward(const float *p, const float *dpc, float *dp) {
+  float n = fmaxf(fmaxf(fabsf(p[0]), fabsf(p[1])), fabsf(p[2]));
+  if (n < 1e-6f) n = 1e-6f;
+  if (n <= 1.0f) { dp[0] = dpc[0]; dp[1] = dpc[1]; dp[2] = dpc[2]; return; }
+  float s = (2 * n - 1) / (n * n), ds = -2 / (n * n) + 2 / (n * n * n);
+  float dot = dpc[0] * p[0] + dpc[1] * p[1] + dpc[2] * p[2];
+  int j = 0;
+  if (fabsf(p[1]) > fabsf(p[j])) j = 1;
+  if (fabsf(p[2]) > fabsf(p[j])) j = 2;
+  for (int a = 0; a < 3; ++a) dp[a] = s * dpc[a];
+  dp[j] += (p[j] >= 0 ? 1.0f : -1.0f) * ds * dot;
+}
+
+void orc_field_backward(const OrcField *f, const float *rays, int64_t N, const float *z, int32_t S,
+                        int white_bg, const float *g_rgb, const float *g_depth, OrcGrads *G,
+                        float *d_rays) {
+  const int A = f->app_dim, Fc = f->featureC, NFt = f->n_acomp[0] + f->n_acomp[1] + f->n_acomp[2];
+  float inv_aabb[3];
+  for (int a = 0; a < 3; ++a) inv_aabb[a] = 2.0f / (f->aabb[3 + a] - f->aabb[a]);
+  float *alpha = malloc(sizeof(float) * S), *w = malloc(sizeof(float) * S), *T = malloc(sizeof(float) * S);
+  float *fe = malloc(sizeof(float) * S), *gw = malloc(sizeof(float) * S);
+  float *praw = malloc(sizeof(float) * 3 * S), *qn = malloc(sizeof(float) * 3 * S);
+  unsigned char *valid = malloc(S);
+  float *prod = malloc(sizeof(float) * NFt), *a27 = malloc(sizeof(float) * A);
+  float *h1 = malloc(sizeof(float) * Fc), *h2 = malloc(sizeof(float) * Fc);
+  float *dh1 = malloc(sizeof(float) * Fc), *dh2 = malloc(sizeof(float) * Fc);
+  float *da27 = malloc(sizeof(float) * A), *dprod = malloc(sizeof(float) * NFt);
+  float pc[ORC_MAX_COMP], lc[ORC_MAX_COMP];
+  for (int64_t r = 0; r < N; ++r) {
+    const float *o = rays + 6 * r, *d = o + 3;
+    const float gr[3] = {g_rgb[3 * r], g_rgb[3 * r + 1], g_rgb[3 * r + 2]};
+    const float gd = g_depth[r];
+    float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    float vd[3] = {d[0] / nrm, d[1] / nrm, d[2] / nrm};
+    /* ---- forward recompute ---- */
+    for (int k = 0; k < S; ++k) {
+      float *p = praw + 3 * k, c3[3];
+      for (int a = 0; a < 3; ++a) { p[a] = o[a] + vd[a] * z[k]; c3[a] = p[a]; }
+      contract3(c3);
+      int ok = 1;
+      if (f->alpha_vol) ok = alpha_mask1(f, c3) > 0.0f;
+      if (k == S - 1) ok = 0;
+      valid[k] = (unsigned char)ok;
+      for (int a = 0; a < 3; ++a) qn[3 * k + a] = (c3[a] - f->aabb[a]) * inv_aabb[a] - 1.0f;
+      fe[k] = ok ? density_feature1(f, qn + 3 * k) : 0.0f;
+      float sigma = ok ? feature2density(f, fe[k]) : 0.0f;
+      float dist = (k < S - 1) ? z[k + 1] - z[k] : 0.0f;
+      alpha[k] = 1.0f - expf(-sigma * dist * f->distance_scale);
+    }
+    alpha[S - 1] = 1.0f;
+    float Tr = 1.0f, acc = 0, dsum = 0;
+    for (int k = 0; k < S; ++k) {
+      T[k] = Tr; w[k] = alpha[k] * Tr; Tr *= (1.0f - alpha[k]) + 1e-10f;
+      acc += w[k]; dsum += w[k] * z[k];
+    }
+    float depth = dsum / nrm;
+    (void)acc;
+    float d_o[3] = {0, 0, 0}, d_vd[3] = {0, 0, 0};
+    /* ---- colour branch: MLP backward per shaded sample; records g . rgb_k for dL/dw ---- */
+    for (int k = 0; k < S; ++k) {
+      gw[k] = (white_bg ? -(gr[0] + gr[1] + gr[2]) : 0.0f) + gd * z[k] / nrm;
+      if (!(w[k] > f->weight_thres)) continue;
+      const float *q = qn + 3 * k;
+      int n = 0;
+      for (int i = 0; i < 3; ++i) {
+        int W = f->grid[MAT0[i]], H = f->grid[MAT1[i]], L = f->grid[VEC[i]], C = f->n_acomp[i];
+        bilinear_plane(f->aplane[i], C, H, W, q[MAT0[i]], q[MAT1[i]], pc);
+        linear_line(f->aline[i], C, L, q[VEC[i]], lc);
+        for (int c = 0; c < C; ++c) prod[n++] = pc[c] * lc[c];
+      }
+      for (int j = 0; j < A; ++j) { float s = 0; for (int t = 0; t < NFt; ++t) s += f->basis[(size_t)j * NFt + t] * prod[t]; a27[j] = s; }
+      for (int nn = 0; nn < Fc; ++nn) { float s = f->b1[nn]; for (int j = 0; j < A; ++j) s += f->w1[(size_t)nn * A + j] * a27[j]; h1[nn] = s > 0 ? s : 0; }
+      for (int nn = 0; nn < Fc; ++nn) { float s = f->b2[nn]; for (int j = 0; j < Fc; ++j) s += f->w2[(size_t)nn * Fc + j] * h1[j]; h2[nn] = s > 0 ? s : 0; }
+      float rgb[3], dpre[3];
+      for (int c = 0; c < 3; ++c) {
+        const float *w3 = f->w3 + (size_t)c * (Fc + 3);
+        float s = f->b3[c];
+        for (int j = 0; j < Fc; ++j) s += w3[j] * h2[j];
+        s += w3[Fc] * vd[0] + w3[Fc + 1] * vd[1] + w3[Fc + 2] * vd[2];
+        rgb[c] = sigmoidf_(s);
+        dpre[c] = gr[c] * w[k] * rgb[c] * (1.0f - rgb[c]);
+        gw[k] += gr[c] * rgb[c];
+      }
+      for (int j = 0; j < Fc; ++j) dh2[j] = 0;
+      for (int c = 0; c < 3; ++c) {
+        float *gw3 = G->w3 + (size_t)c * (Fc + 3);
+        const float *w3 = f->w3 + (size_t)c * (Fc + 3);
+        G->b3[c] += dpre[c];
+        for (int j = 0; j < Fc; ++j) { gw3[j] += dpre[c] * h2[j]; dh2[j] += w3[j] * dpre[c]; }
+        for (int a = 0; a < 3; ++a) gw3[Fc + a] += dpre[c] * vd[a];      /* viewdirs are detached (:628) */
+      }
+      for (int j = 0; j < Fc; ++j) dh1[j] = 0;
+      for (int nn = 0; nn < Fc; ++nn) {
+        float gpre = h2[nn] > 0 ? dh2[nn] : 0.0f;
+        if (gpre == 0.0f) continue;
+        G->b2[nn] += gpre;
+        for (int j = 0; j < Fc; ++j) { G->w2[(size_t)nn * Fc + j] += gpre * h1[j]; dh1[j] += f->w2[(size_t)nn * Fc + j] * gpre; }
+      }
+      for (int j = 0; j < A; ++j) da27[j] = 0;
+      for (int nn = 0; nn < Fc; ++nn) {
+        float gpre = h1[nn] > 0 ? dh1[nn] : 0.0f;
+        if (gpre == 0.0f) continue;
+        G->b1[nn] += gpre;
+        for (int j = 0; j < A; ++j) { G->w1[(size_t)nn * A + j] += gpre * a27[j]; da27[j] += f->w1[(size_t)nn * A + j] * gpre; }
+      }
+      for (int t = 0; t < NFt; ++t) dprod[t] = 0;
+      for (int j = 0; j < A; ++j)
+        for (int t = 0; t < NFt; ++t) { G->basis[(size_t)j * NFt + t] += da27[j] * prod[t]; dprod[t] += f->basis[(size_t)j * NFt + t] * da27[j]; }
+      float dq[3] = {0, 0, 0};
+      n = 0;
+      for (int i = 0; i < 3; ++i) {
+        vm_pair_backward(f->grid, i, f->n_acomp[i], f->aplane[i], f->aline[i], G->aplane[i], G->aline[i], q, dprod + n, 1, dq);
+        n += f->n_acomp[i];
+      }
+      float dpc[3], dp[3];
+      for (int a = 0; a < 3; ++a) dpc[a] = dq[a] * inv_aabb[a];
+      contract_backward(praw + 3 * k, dpc, dp);
+      for (int a = 0; a < 3; ++a) { d_o[a] += dp[a]; d_vd[a] += dp[a] * z[k]; }
+    }
+    /* ---- density branch: dL/dw -> dL/dalpha (suffix sums) -> sigma -> feature -> grids, position ---- */
+    float suffix = 0.0f;
+    for (int k = S - 1; k >= 0; --k) {
+      float dalpha = gw[k] * T[k] - suffix / ((1.0f - alpha[k]) + 1e-10f);
+      suffix += gw[k] * w[k];
+      if (k == S - 1 || !valid[k]) continue;             /* alpha[:, -1] = 1 and masked samples: constants */
+      float dist = z[k + 1] - z[k];
+      float dsigma = dalpha * (1.0f - alpha[k]) * dist * f->distance_scale;
+      float x = fe[k] + f->density_shift, df;
+      if (f->act == 0) df = dsigma * (x > 20.0f ? 1.0f : sigmoidf_(x));
+      else df = fe[k] > 0.0f ? dsigma : 0.0f;
+      if (df == 0.0f) continue;
+      float dq[3] = {0, 0, 0};
+      float g1[ORC_MAX_COMP];
+      for (int c = 0; c < ORC_MAX_COMP; ++c) g1[c] = df;
+      for (int i = 0; i < 3; ++i)
+        vm_pair_backward(f->grid, i, f->n_dcomp[i], f->dplane[i], f->dline[i], G->dplane[i], G->dline[i], qn + 3 * k, g1, 1, dq);
+      float dpc[3], dp[3];
+      for (int a = 0; a < 3; ++a) dpc[a] = dq[a] * inv_aabb[a];
+      contract_backward(praw + 3 * k, dpc, dp);
+      for (int a = 0; a < 3; ++a) { d_o[a] += dp[a]; d_vd[a] += dp[a] * z[k]; }
+    }
+    /* ---- rays: vd = d/|d| and depth = sum(w z)/|d| ---- */
+    float dotv = vd[0] * d_vd[0] + vd[1] * d_vd[1] + vd[2] * d_vd[2];
+    for (int a = 0; a < 3; ++a) {
+      d_rays[6 * r + a] = d_o[a];
+      d_rays[6 * r + 3 + a] = (d_vd[a] - vd[a] * dotv) / nrm - gd * depth / nrm * vd[a];
+    }
+  }
+  free(alpha); free(w); free(T); free(fe); free(gw); free(praw); free(qn); free(valid);
+  free(prod); free(a27); free(h1); free(h2); free(dh1); free(dh2); free(da27); free(dprod);
+}

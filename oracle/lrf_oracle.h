@@ -85,6 +85,20 @@ void orc_local_forward(const OrcField *fields, int32_t n_fields, const float *co
                        int white_bg, float floater_thresh, int refine, float *rgb, float *depth,
                        float *dirs, int n_threads);
 
+/* Gradients of TensorBase.forward (what torch autograd computes through tensorBase.py:567-636 with
+ * floater_thresh = 0): given dL/d(rgb_map) [N][3] and dL/d(depth_map) [N], accumulates dL/d(parameter)
+ * into the OrcGrads buffers (reference layouts, caller zero-initialises) and writes dL/d(rays) [N][6].
+ * Pinned against the reference's own autograd (tests/golden/grads_field.npz).  The checker for the
+ * fused backward kernel (SURVEY.md par. 8f rank 1). */
+typedef struct OrcGrads {
+  float *dplane[3], *dline[3], *aplane[3], *aline[3];
+  float *basis, *w1, *b1, *w2, *b2, *w3, *b3;
+} OrcGrads;
+
+void orc_field_backward(const OrcField *f, const float *rays, int64_t N, const float *z, int32_t S,
+                        int white_bg, const float *g_rgb, const float *g_depth, OrcGrads *grads,
+                        float *d_rays);
+
 #ifdef __cplusplus
 }
 #endif

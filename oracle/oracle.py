@@ -45,6 +45,12 @@ class OrcField(C.Structure):
     ]
 
 
+class OrcGrads(C.Structure):
+    _fields_ = [("dplane", _fp * 3), ("dline", _fp * 3), ("aplane", _fp * 3), ("aline", _fp * 3),
+                ("basis", _fp), ("w1", _fp), ("b1", _fp), ("w2", _fp), ("b2", _fp), ("w3", _fp),
+                ("b3", _fp)]
+
+
 def build(force=False):
     """Compile oracle/lrf_oracle.c -> oracle/liblrf_oracle.so (recipe == oracle/Makefile)."""
     src = os.path.join(_HERE, "lrf_oracle.c")
@@ -88,6 +94,9 @@ def lib():
             C.POINTER(C.c_int64), C.c_int64, C.c_int32, C.c_int32, C.c_int, C.c_float, C.c_float,
             C.c_float, _fp, C.c_int64, _fp, _fp, _fp, C.c_int, C.c_float, C.c_int, _fp, _fp, _fp,
             C.c_int]
+        L.orc_field_backward.argtypes = [
+            C.POINTER(OrcField), _fp, C.c_int64, _fp, C.c_int32, C.c_int, _fp, _fp,
+            C.POINTER(OrcGrads), _fp]
         _lib = L
     return _lib
 
@@ -266,3 +275,29 @@ def local_forward(fields, zs, ray_ids, W, H, fov360, focal, cx, cy, cam2world, w
                             float(floater_thresh), int(bool(refine)), _p(rgb), _p(depth), _p(dirs),
                             int(n_threads))
     return dict(rgb=rgb, depth=depth, directions=dirs)
+
+
+def field_backward(field, fd, rays, z, g_rgb, g_depth, white_bg=True):
+    """Analytic gradients of TensorBase.forward (floater 0) -> dict keyed like the reference's
+    named_parameters (reference layouts) plus "rays".  `fd` is the field dict `field` was built from
+    (for the parameter shapes)."""
+    r = _f32(rays).reshape(-1, 6); z = _f32(z).reshape(-1)
+    gr = _f32(g_rgb).reshape(-1, 3); gd = _f32(g_depth).reshape(-1)
+    out = {}
+    G = OrcGrads()
+
+    def buf(key):
+        a = np.zeros(np.asarray(fd[key]).shape, np.float32); out[key] = a; return _p(a)
+
+    for i in range(3):
+        G.dplane[i] = buf(f"density_plane.{i}"); G.dline[i] = buf(f"density_line.{i}")
+        G.aplane[i] = buf(f"app_plane.{i}"); G.aline[i] = buf(f"app_line.{i}")
+    G.basis = buf("basis_mat.weight")
+    G.w1, G.b1 = buf("renderModule.mlp.0.weight"), buf("renderModule.mlp.0.bias")
+    G.w2, G.b2 = buf("renderModule.mlp.2.weight"), buf("renderModule.mlp.2.bias")
+    G.w3, G.b3 = buf("renderModule.mlp_view.0.weight"), buf("renderModule.mlp_view.0.bias")
+    d_rays = np.zeros_like(r)
+    lib().orc_field_backward(C.byref(field.struct), _p(r), r.shape[0], _p(z), z.shape[0],
+                             int(bool(white_bg)), _p(gr), _p(gd), C.byref(G), _p(d_rays))
+    out["rays"] = d_rays
+    return out
