@@ -346,8 +346,9 @@ int lrf_render_backward(const LrfField* f, const void* prepared_bwd, const float
   for (int i = 0; i < 3; ++i) {
     if (!g->d_dplane[i] || !g->d_dline[i] || !g->d_aplane[i] || !g->d_aline[i])
       return fail(LRF_ERR_INVALID, "gradient buffer is NULL");
-    if (((uintptr_t)g->d_dplane[i] | (uintptr_t)g->d_dline[i]) & 15)
-      return fail(LRF_ERR_INVALID, "density gradient buffers must be 16-byte aligned");
+    if (((uintptr_t)g->d_dplane[i] | (uintptr_t)g->d_dline[i] | (uintptr_t)g->d_aplane[i] |
+         (uintptr_t)g->d_aline[i]) & 15)
+      return fail(LRF_ERR_INVALID, "plane/line gradient buffers must be 16-byte aligned");
   }
   if (!scratch || ((uintptr_t)scratch & 15)) return fail(LRF_ERR_INVALID, "scratch is NULL or not 16-byte aligned");
   if (scratch_bytes < lrf::backward_scratch_bytes(n_rays, F.S))

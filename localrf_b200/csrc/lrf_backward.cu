@@ -310,24 +310,20 @@ bwd_shade_kernel(const FieldDev F, const BwdArgs A) {
         grid_coord(qq[mat0(i)], W, x0, x1, tx);
         grid_coord(qq[mat1(i)], H, y0, y1, ty);
         grid_coord(qq[vecm(i)], Ln, l0, l1, tl);
-        const float* P = F.aplane[i] + cq * 6;
-        const float* Lp = F.aline[i] + cq * 6;
-        const size_t o00 = ((size_t)y0 * W + x0) * CA, o01 = ((size_t)y0 * W + x1) * CA;
-        const size_t o10 = ((size_t)y1 * W + x0) * CA, o11 = ((size_t)y1 * W + x1) * CA;
-#pragma unroll
-        for (int e = 0; e < 6; e += 2) {
-          const float2 a = __ldg(reinterpret_cast<const float2*>(P + o00 + e));
-          const float2 b = __ldg(reinterpret_cast<const float2*>(P + o01 + e));
-          const float2 c = __ldg(reinterpret_cast<const float2*>(P + o10 + e));
-          const float2 d = __ldg(reinterpret_cast<const float2*>(P + o11 + e));
-          const float2 u = __ldg(reinterpret_cast<const float2*>(Lp + (size_t)l0 * CA + e));
-          const float2 v = __ldg(reinterpret_cast<const float2*>(Lp + (size_t)l1 * CA + e));
-          const float P0 = a.x * (1.0f - tx) * (1.0f - ty) + b.x * tx * (1.0f - ty) + c.x * (1.0f - tx) * ty + d.x * tx * ty;
-          const float P1 = a.y * (1.0f - tx) * (1.0f - ty) + b.y * tx * (1.0f - ty) + c.y * (1.0f - tx) * ty + d.y * tx * ty;
-          const float L0 = u.x * (1.0f - tl) + v.x * tl;
-          const float L1 = u.y * (1.0f - tl) + v.y * tl;
-          X_s[ls * LDX + i * CA + cq * 6 + e] = ls < n_valid ? P0 * L0 : 0.0f;
-          X_s[ls * LDX + i * CA + cq * 6 + e + 1] = ls < n_valid ? P1 * L1 : 0.0f;
+        const float w00 = (1.0f - tx) * (1.0f - ty), w01 = tx * (1.0f - ty);
+        const float w10 = (1.0f - tx) * ty, w11 = tx * ty, u0 = 1.0f - tl;
+        for (int grp = cq; grp < CA / 4; grp += 4) {                    // 4 components per 16-byte group
+          const float* P = F.aplane[i] + grp * 4;
+          const float* Lp = F.aline[i] + grp * 4;
+          const float4 a = ldg4(P + ((size_t)y0 * W + x0) * CA), b = ldg4(P + ((size_t)y0 * W + x1) * CA);
+          const float4 c = ldg4(P + ((size_t)y1 * W + x0) * CA), d = ldg4(P + ((size_t)y1 * W + x1) * CA);
+          const float4 u = ldg4(Lp + (size_t)l0 * CA), v = ldg4(Lp + (size_t)l1 * CA);
+          float* xo = X_s + ls * LDX + i * CA + grp * 4;
+          const bool ok = ls < n_valid;
+          xo[0] = ok ? (a.x * w00 + b.x * w01 + c.x * w10 + d.x * w11) * (u.x * u0 + v.x * tl) : 0.0f;
+          xo[1] = ok ? (a.y * w00 + b.y * w01 + c.y * w10 + d.y * w11) * (u.y * u0 + v.y * tl) : 0.0f;
+          xo[2] = ok ? (a.z * w00 + b.z * w01 + c.z * w10 + d.z * w11) * (u.z * u0 + v.z * tl) : 0.0f;
+          xo[3] = ok ? (a.w * w00 + b.w * w01 + c.w * w10 + d.w * w11) * (u.w * u0 + v.w * tl) : 0.0f;
         }
       }
     }
@@ -444,9 +440,13 @@ bwd_shade_kernel(const FieldDev F, const BwdArgs A) {
     __syncthreads();
     // ---- 2f. layer 2 backward: db2, dW2 += dh2^T h1, dh1 = dh2 W2 ------------------------------------
     if (tid < FC) {
-      float s2 = 0.0f;
-      for (int s = 0; s < TS; ++s) s2 += H2_s[s * LDW + tid];
-      accB2 += s2;
+      float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+#pragma unroll 4
+      for (int s = 0; s < TS; s += 4) {
+        p0 += H2_s[s * LDW + tid]; p1 += H2_s[(s + 1) * LDW + tid];
+        p2 += H2_s[(s + 2) * LDW + tid]; p3 += H2_s[(s + 3) * LDW + tid];
+      }
+      accB2 += (p0 + p1) + (p2 + p3);
     }
     for (int s = 0; s < TS; ++s) {
       float dv[8], hv[8];
@@ -488,9 +488,13 @@ bwd_shade_kernel(const FieldDev F, const BwdArgs A) {
     __syncthreads();
     // ---- 2g. layer 1 backward: db1, dW1B += dh1^T x, dprod = dh1 W1B -----------------------------------
     if (tid < FC) {
-      float s1 = 0.0f;
-      for (int s = 0; s < TS; ++s) s1 += H1_s[s * LDW + tid];
-      accB1 += s1;
+      float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+#pragma unroll 4
+      for (int s = 0; s < TS; s += 4) {
+        p0 += H1_s[s * LDW + tid]; p1 += H1_s[(s + 1) * LDW + tid];
+        p2 += H1_s[(s + 2) * LDW + tid]; p3 += H1_s[(s + 3) * LDW + tid];
+      }
+      accB1 += (p0 + p1) + (p2 + p3);
     }
     for (int s = 0; s < TS; ++s) {
       float dv[8], xv[5];
@@ -528,7 +532,7 @@ bwd_shade_kernel(const FieldDev F, const BwdArgs A) {
           if (tn + 16 * j < NF) X_s[(4 * ts + i) * LDX + tn + 16 * j] = acc[i][j];
     }
     __syncthreads();
-    // ---- 2h. products backward: appearance planes / lines, sample position -> ray ---------------------
+    // ---- 2h. products backward: appearance planes / lines (16-byte reductions), position -> ray -----
     {
       float dq0 = 0.0f, dq1 = 0.0f, dq2 = 0.0f;
       if (ls < n_valid) {
@@ -541,29 +545,35 @@ bwd_shade_kernel(const FieldDev F, const BwdArgs A) {
           coord_g(qq[mat0(i)], W, x0, x1, tx, dx);
           coord_g(qq[mat1(i)], H, y0, y1, ty, dy);
           coord_g(qq[vecm(i)], Ln, l0, l1, tl, dl);
-          const size_t o00 = ((size_t)y0 * W + x0) * CA + cq * 6, o01 = ((size_t)y0 * W + x1) * CA + cq * 6;
-          const size_t o10 = ((size_t)y1 * W + x0) * CA + cq * 6, o11 = ((size_t)y1 * W + x1) * CA + cq * 6;
-          const size_t ol0 = (size_t)l0 * CA + cq * 6, ol1 = (size_t)l1 * CA + cq * 6;
           const float w00 = (1.0f - tx) * (1.0f - ty), w01 = tx * (1.0f - ty);
-          const float w10 = (1.0f - tx) * ty, w11 = tx * ty;
+          const float w10 = (1.0f - tx) * ty, w11 = tx * ty, u0 = 1.0f - tl;
           float gx = 0.0f, gy = 0.0f, gl = 0.0f;
+          for (int grp = cq; grp < CA / 4; grp += 4) {                  // 4 components per 16-byte group
+            const size_t o00 = ((size_t)y0 * W + x0) * CA + grp * 4, o01 = ((size_t)y0 * W + x1) * CA + grp * 4;
+            const size_t o10 = ((size_t)y1 * W + x0) * CA + grp * 4, o11 = ((size_t)y1 * W + x1) * CA + grp * 4;
+            const size_t ol0 = (size_t)l0 * CA + grp * 4, ol1 = (size_t)l1 * CA + grp * 4;
+            const float4 a4 = ldg4(F.aplane[i] + o00), b4 = ldg4(F.aplane[i] + o01);
+            const float4 c4 = ldg4(F.aplane[i] + o10), d4 = ldg4(F.aplane[i] + o11);
+            const float4 u4 = ldg4(F.aline[i] + ol0), v4 = ldg4(F.aline[i] + ol1);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float uv[4] = {u4.x, u4.y, u4.z, u4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+            float dP[4], dL[4];
 #pragma unroll
-          for (int e = 0; e < 6; ++e) {
-            const float a = __ldg(F.aplane[i] + o00 + e), b = __ldg(F.aplane[i] + o01 + e);
-            const float c = __ldg(F.aplane[i] + o10 + e), d = __ldg(F.aplane[i] + o11 + e);
-            const float u = __ldg(F.aline[i] + ol0 + e), v = __ldg(F.aline[i] + ol1 + e);
-            const float gc = X_s[ls * LDX + i * CA + cq * 6 + e];
-            const float dP = gc * (u * (1.0f - tl) + v * tl);
-            const float dL = gc * (a * w00 + b * w01 + c * w10 + d * w11);
-            atomicAdd(A.d_aplane[i] + o00 + e, dP * w00);
-            atomicAdd(A.d_aplane[i] + o01 + e, dP * w01);
-            atomicAdd(A.d_aplane[i] + o10 + e, dP * w10);
-            atomicAdd(A.d_aplane[i] + o11 + e, dP * w11);
-            atomicAdd(A.d_aline[i] + ol0 + e, dL * (1.0f - tl));
-            atomicAdd(A.d_aline[i] + ol1 + e, dL * tl);
-            gx += dP * ((b - a) * (1.0f - ty) + (d - c) * ty);
-            gy += dP * ((c - a) * (1.0f - tx) + (d - b) * tx);
-            gl += dL * (v - u);
+            for (int e = 0; e < 4; ++e) {
+              const float gc = X_s[ls * LDX + i * CA + grp * 4 + e];
+              dP[e] = gc * (uv[e] * u0 + vv[e] * tl);
+              dL[e] = gc * (av[e] * w00 + bv[e] * w01 + cv[e] * w10 + dv[e] * w11);
+              gx += dP[e] * ((bv[e] - av[e]) * (1.0f - ty) + (dv[e] - cv[e]) * ty);
+              gy += dP[e] * ((cv[e] - av[e]) * (1.0f - tx) + (dv[e] - bv[e]) * tx);
+              gl += dL[e] * (vv[e] - uv[e]);
+            }
+            red4g(A.d_aplane[i] + o00, dP[0] * w00, dP[1] * w00, dP[2] * w00, dP[3] * w00);
+            red4g(A.d_aplane[i] + o01, dP[0] * w01, dP[1] * w01, dP[2] * w01, dP[3] * w01);
+            red4g(A.d_aplane[i] + o10, dP[0] * w10, dP[1] * w10, dP[2] * w10, dP[3] * w10);
+            red4g(A.d_aplane[i] + o11, dP[0] * w11, dP[1] * w11, dP[2] * w11, dP[3] * w11);
+            red4g(A.d_aline[i] + ol0, dL[0] * u0, dL[1] * u0, dL[2] * u0, dL[3] * u0);
+            red4g(A.d_aline[i] + ol1, dL[0] * tl, dL[1] * tl, dL[2] * tl, dL[3] * tl);
           }
           dq[mat0(i)] += gx * dx; dq[mat1(i)] += gy * dy; dq[vecm(i)] += gl * dl;
         }
