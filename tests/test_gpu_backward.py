@@ -84,30 +84,59 @@ def _batch_rays(n, seed):
     return torch.cat([o, d], -1).cuda()
 
 
+def _l2_err(a, b):
+    a = a.double(); b = b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
 def test_fused_backward_matches_composed_path_fullsize(field300, monkeypatch):
     """4096 rays at 300^3 / S = 344: every parameter gradient and d(rays) of the fused backward
-    against autograd through the composed path (CUDA lookups + torch ops) on the same inputs."""
+    against autograd through the composed path (CUDA lookups + torch ops) on the same inputs.
+
+    The composed path computes alpha = 1 - exp(-x) like the reference (6e-5 relative noise at
+    x ~ 1e-3) where the kernels use expm1, and that noise moves ~1 % of the rays' samples across the
+    hard weight > rayMarch_weight_thres shading switch (tensorBase.py:622).  A grid cell only sums
+    ~15 samples, so one switched sample is visible in a max-norm comparison.  Hence two runs: with the
+    threshold at 0 (every sample shaded in both paths, nothing to switch) the comparison is tight; at
+    the default 1e-3 the outputs agree except on those rays and the gradients agree in the L2 sense."""
     m = field300
     rays = _batch_rays(4096, 5)
     z = m.sample_table(True, -1, rays.device)
     g = torch.Generator().manual_seed(2)
     c_rgb = torch.randn(4096, 3, generator=g).cuda()
     c_depth = (0.05 * torch.randn(4096, generator=g)).cuda()
-    monkeypatch.setenv("LRF_TRAIN_PATH", "composed")
-    ref, rgb_c, depth_c = _grads(m, rays, z, c_rgb, c_depth, True)
-    monkeypatch.setenv("LRF_TRAIN_PATH", "fused")
-    _no_composed(m, monkeypatch)
-    got, rgb_f, depth_f = _grads(m, rays, z, c_rgb, c_depth, True)
-    # The composed path computes alpha = 1 - exp(-x) like the reference (6e-5 relative noise at
-    # x ~ 1e-3); the kernel uses expm1.  That noise moves ~1 % of the rays' samples across the hard
-    # weight > 1e-3 shading threshold (tensorBase.py:622); one such sample changes rgb by <= ~1e-3.
-    d_rgb = (rgb_f - rgb_c).abs().max(dim=-1).values
-    fwd = dict(median=float(d_rgb.median()), frac=float((d_rgb > 5e-5).float().mean()), max=float(d_rgb.max()))
-    assert fwd["median"] < 5e-6 and fwd["frac"] < 0.05 and fwd["max"] < 3e-3, fwd
+    composed = m._forward_autograd
+
+    def both(n):
+        monkeypatch.setenv("LRF_TRAIN_PATH", "composed")
+        monkeypatch.setattr(m, "_forward_autograd", composed)
+        ref = _grads(m, rays[:n], z, c_rgb[:n], c_depth[:n], True)
+        monkeypatch.setenv("LRF_TRAIN_PATH", "fused")
+        _no_composed(m, monkeypatch)
+        return ref, _grads(m, rays[:n], z, c_rgb[:n], c_depth[:n], True)
+
+    thres = m.rayMarch_weight_thres
+    try:
+        m.rayMarch_weight_thres = 0.0
+        (ref, rgb_c, depth_c), (got, rgb_f, depth_f) = both(2048)       # 0.7 M shaded samples
+    finally:
+        m.rayMarch_weight_thres = thres
+    assert rel_err(rgb_f.cpu().numpy(), rgb_c.cpu().numpy()) < 1e-4
     assert rel_err(depth_f.cpu().numpy(), depth_c.cpu().numpy()) < 1e-4
     assert set(ref) == set(got) and len(got) == 20
     errs = {key: scale_err(got[key].cpu().numpy(), ref[key].cpu().numpy()) for key in ref}
-    assert max(errs.values()) < 1e-3, errs          # includes the threshold-crossing samples above
+    print("thres 0, max-norm errors:", {k: f"{v:.1e}" for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+
+    (ref, rgb_c, depth_c), (got, rgb_f, depth_f) = both(4096)
+    d_rgb = (rgb_f - rgb_c).abs().max(dim=-1).values
+    fwd = dict(median=float(d_rgb.median()), frac=float((d_rgb > 5e-5).float().mean()), max=float(d_rgb.max()))
+    print("default thres, forward:", fwd)
+    assert fwd["median"] < 5e-6 and fwd["frac"] < 0.05 and fwd["max"] < 3e-3, fwd
+    assert rel_err(depth_f.cpu().numpy(), depth_c.cpu().numpy()) < 1e-4
+    l2 = {key: _l2_err(got[key], ref[key]) for key in ref}
+    print("default thres, relative L2 errors:", {k: f"{v:.1e}" for k, v in l2.items()})
+    assert max(l2.values()) < 2e-2, l2
 
 
 def test_backward_linear_in_upstream_and_order_independent(field300, monkeypatch):
