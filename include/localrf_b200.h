@@ -142,7 +142,7 @@ int lrf_density_feature(const LrfField *field, const float *xyz_norm, int64_t M,
 int lrf_app_feature(const LrfField *field, const float *xyz_norm, int64_t M, float *out,
                     lrf_stream_t stream);
 
-/* ---- training path (first step): differentiable lookups ------------------
+/* ---- differentiable lookups (the composed training path) -------------------
  * The 72 plane x line products of compute_appfeature BEFORE basis_mat (tensoRF.py:174-194 order):
  * xyz_norm [M][3] -> out [M][3*n_acomp]. */
 int lrf_app_products(const LrfField *field, const float *xyz_norm, int64_t M, float *out,

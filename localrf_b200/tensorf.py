@@ -542,9 +542,10 @@ class TensorBase(torch.nn.Module):
                           return_weights, z_vals):
         """The composed path: the same algorithm as the fused kernel, built from the two
         differentiable CUDA lookups (`_VMLookup`: density feature, appearance products) and torch ops
-        for the cheap per-sample arithmetic and the dense MLP.  Used when autograd is recording
-        (training: gradients reach planes, lines, basis, MLP and the rays, hence poses and
-        intrinsics) and for configurations the fused kernel does not cover.  tensorBase.py:567-636."""
+        for the cheap per-sample arithmetic and the dense MLP; differentiable end to end.  Used for
+        configurations the fused kernels do not cover (positional encodings; floater filter or
+        `return_weights` while autograd records) and, with LRF_TRAIN_PATH=composed, as the independent
+        implementation the fused backward is compared with.  tensorBase.py:567-636."""
         from .ray_utils import contract
         dev = rays_chunk.device
         rays_o, d = rays_chunk[:, :3], rays_chunk[:, 3:6]
