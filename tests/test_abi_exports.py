@@ -49,3 +49,21 @@ def test_validation_errors_without_gpu():
     assert rc == -1                       # gridSize 0
     rc = L.lrf_render(C.byref(f), None, None, None, None)
     assert rc == -1
+
+
+def test_backward_sizes_and_validation_without_gpu():
+    L = _lib.lib()
+    # (W1 @ basis)^T [72][128], W2^T [128][128], b1, b2, W3 [3][132], b3 [4] in fp32
+    assert L.lrf_prepared_backward_bytes() == 4 * (72 * 128 + 128 * 128 + 128 + 128 + 3 * 132 + 4)
+    n, S = 4096, 344
+    need = L.lrf_backward_scratch_bytes(n, S)
+    # 5 fp32 tables + 2 int32 lists + 1 byte per sample, the per-ray accumulators and the counter
+    assert need % 16 == 0 and n * S * 29 + n * 24 + 16 <= need <= n * S * 29 + n * 24 + 16 + 16 * 10
+    assert L.lrf_backward_scratch_bytes(2 * n, S) > need
+    assert L.lrf_backward_scratch_bytes(-1, S) == 0 and L.lrf_backward_scratch_bytes(n, 1) == 0
+    assert C.sizeof(_lib.LrfGradients) == 19 * 8
+    f = _lib.LrfField()
+    rc = L.lrf_render_backward(C.byref(f), None, None, 0, 0, None, None, None, None, 0, None)
+    assert rc == -1 and b"prepared_bwd" in L.lrf_last_error()
+    rc = L.lrf_field_prepare_backward(C.byref(f), None, None)
+    assert rc == -1
