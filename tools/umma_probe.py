@@ -84,7 +84,7 @@ def main():
     dev = torch.device("cuda", 0)
     rng = np.random.default_rng(0)
     results = []
-    for K, N in ((64, 128), (128, 128), (128, 80), (128, 96)):
+    for K, N in ((64, 128), (128, 128), (128, 80), (128, 96), (128, 16)):
         A = rng.integers(-3, 4, (128, K)).astype(np.float32)
         B = rng.integers(-3, 4, (N, K)).astype(np.float32)
         want = A @ B.T
