@@ -94,8 +94,12 @@ umma_probe_kernel(const ProbeParams P, const unsigned char* __restrict__ a_img,
     }
     umma_commit(bar);
   }
-  mbar_wait(bar, 0);
+  bool done = false;                               // bounded wait: a setting the hardware rejects must not hang the box
+  for (int it = 0; it < (1 << 22) && !done; ++it) done = mbar_try(bar, 0);
   tc_fence_after();
+  if (!done) {
+    if (tid == 0) out[0] = -12345.0f;              // sentinel: the MMAs never completed
+  } else
   for (int c0 = 0; c0 < P.N; c0 += 32) {
     float v[32];
     tmem_ld32(t_row + (uint32_t)c0, v);
