@@ -164,7 +164,7 @@ bwd_march_kernel(const FieldDev F, const BwdArgs A) {
         float sigma = 0.0f;
         if (valid) { fe = density_feature(F, q); sigma = feature2density(fe, F.density_shift, F.act); }
         const float znext = (k + 1 < S) ? __ldg(F.z + k + 1) : z;
-        alpha = -expm1f(-sigma * (znext - z) * F.distance_scale);
+        alpha = 1.0f - expf(-sigma * (znext - z) * F.distance_scale);   // tensorBase.py:610
         if (k == S - 1) alpha = 1.0f;                                  // alpha[:, -1] = 1
       }
       const float f = (k < S) ? (1.0f - alpha) + 1e-10f : 1.0f;

@@ -23,10 +23,10 @@
 //       tcgen05.commit signals the consumers and frees the A tile for the producers.
 //   consumers (4 warps, thread = tile row)  epilogue 1: tcgen05.ld acc1, bias + ReLU, re-split,
 //       tcgen05.st as layer 2's A operand; epilogue 2: tcgen05.ld acc2, bias + ReLU, layer 3
-//       (131 -> 3) + sigmoid; composite: w * rgb is added to the row's ray slot IN ROW ORDER (rows
-//       of one ray are allocated in sample order, so every ray's sum has a fixed order: results
-//       are bit-identical whatever the interleaving); the last contributor of a ray writes its
-//       output (white background, blend, accumulate, exposure, clamp).
+//       (131 -> 3) + sigmoid; composite: w * rgb is added to the row's ray slot as 32-bit FIXED
+//       POINT with shared-memory atomics (integer adds are associative, so results are
+//       bit-identical whatever the interleaving of rows, tiles and threads); the last contributor
+//       of a ray writes its output (white background, blend, accumulate, exposure, clamp).
 //
 // The weight operands are staged once per CTA by TMA bulk copies (cp.async.bulk -> UBLKCP).
 #include <cstdlib>
@@ -374,7 +374,7 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
             ++marched;
           }
           const float dist = z_s[k + 1] - z;
-          alpha = -expm1f(-sigma * dist * F.distance_scale);          // 1 - exp(-sigma*dist*scale)
+          alpha = 1.0f - expf(-sigma * dist * F.distance_scale);       // tensorBase.py:610, same form
           if (k == S - 1) alpha = 1.0f;                               // alpha[:, -1] = 1
         }
         const float f = (k < S) ? (1.0f - alpha) + 1e-10f : 1.0f;

@@ -391,12 +391,15 @@ void orc_ray_directions(const int64_t *ray_ids, int64_t N, int32_t W, int32_t H,
 }
 
 /* ---- local_tensorfs.py:382-499  LocalTensorfs.forward() -------------------------------------- */
-void orc_local_forward(const OrcField *fields, int32_t n_fields, const float *const *zs,
-                       const int32_t *Ss, const int64_t *ray_ids, int64_t N, int32_t W, int32_t H,
-                       int fov360, float focal, float cx, float cy, const float *cam2world,
-                       int64_t V, const float *world2rf, const float *blend, const float *exposure,
-                       int white_bg, float floater_thresh, int refine, float *rgb, float *depth,
-                       float *dirs, int n_threads) {
+/* `margin` (optional, [N]): every ray's smallest |w - rayMarch_weight_thres| over the samples of all
+ * active fields -- how close the ray sits to the hard shading switch of tensorBase.py:622 (test
+ * bookkeeping for exact-threshold ties; not part of the reference's outputs). */
+void orc_local_forward_m(const OrcField *fields, int32_t n_fields, const float *const *zs,
+                         const int32_t *Ss, const int64_t *ray_ids, int64_t N, int32_t W, int32_t H,
+                         int fov360, float focal, float cx, float cy, const float *cam2world,
+                         int64_t V, const float *world2rf, const float *blend, const float *exposure,
+                         int white_bg, float floater_thresh, int refine, float *rgb, float *depth,
+                         float *dirs, float *margin, int n_threads) {
   orc_ray_directions(ray_ids, N, W, H, fov360, focal, cx, cy, dirs, NULL);      /* :397-401 */
   int64_t per_view = N / V;                                                      /* :437 */
   float *rays = (float *)malloc(sizeof(float) * 6 * N);
@@ -404,6 +407,13 @@ void orc_local_forward(const OrcField *fields, int32_t n_fields, const float *co
   float *depth_t = (float *)malloc(sizeof(float) * N);
   memset(rgb, 0, sizeof(float) * 3 * N);                                         /* :439-440 */
   memset(depth, 0, sizeof(float) * N);
+  float *w_t = NULL;
+  if (margin) {
+    int32_t Smax = 0;
+    for (int32_t k = 0; k < n_fields; ++k) if (Ss[k] > Smax) Smax = Ss[k];
+    w_t = (float *)malloc(sizeof(float) * (size_t)N * Smax);
+    for (int64_t r = 0; r < N; ++r) margin[r] = 1e30f;
+  }
   for (int32_t k = 0; k < n_fields; ++k) {
     float colsum = 0.0f;                                                         /* :418 */
     for (int64_t v = 0; v < V; ++v) colsum += blend[v * n_fields + k];
@@ -420,7 +430,13 @@ void orc_local_forward(const OrcField *fields, int32_t n_fields, const float *co
       }
     }
     orc_field_forward(&fields[k], rays, N, zs[k], Ss[k], white_bg, floater_thresh, refine, rgb_t,
-                      depth_t, NULL, NULL, NULL, n_threads);                     /* :458-465 */
+                      depth_t, w_t, NULL, NULL, n_threads);                      /* :458-465 */
+    if (margin)
+      for (int64_t r = 0; r < N; ++r)
+        for (int32_t j = 0; j < Ss[k]; ++j) {
+          float m = fabsf(w_t[(size_t)r * Ss[k] + j] - fields[k].weight_thres);
+          if (m < margin[r]) margin[r] = m;
+        }
     for (int64_t r = 0; r < N; ++r) {                                            /* :467-474 */
       float bw = blend[(r / per_view) * n_fields + k];
       for (int a = 0; a < 3; ++a) rgb[3 * r + a] = rgb[3 * r + a] + rgb_t[3 * r + a] * bw;
@@ -441,7 +457,18 @@ void orc_local_forward(const OrcField *fields, int32_t n_fields, const float *co
     }
     for (int a = 0; a < 3; ++a) c[a] = fminf(1.0f, fmaxf(0.0f, c[a]));          /* :497 */
   }
-  free(rays); free(rgb_t); free(depth_t);
+  free(rays); free(rgb_t); free(depth_t); free(w_t);
+}
+
+void orc_local_forward(const OrcField *fields, int32_t n_fields, const float *const *zs,
+                       const int32_t *Ss, const int64_t *ray_ids, int64_t N, int32_t W, int32_t H,
+                       int fov360, float focal, float cx, float cy, const float *cam2world,
+                       int64_t V, const float *world2rf, const float *blend, const float *exposure,
+                       int white_bg, float floater_thresh, int refine, float *rgb, float *depth,
+                       float *dirs, int n_threads) {
+  orc_local_forward_m(fields, n_fields, zs, Ss, ray_ids, N, W, H, fov360, focal, cx, cy, cam2world, V,
+                      world2rf, blend, exposure, white_bg, floater_thresh, refine, rgb, depth, dirs,
+                      NULL, n_threads);
 }
 
 /* =================================================================================================

@@ -84,6 +84,14 @@ void orc_local_forward(const OrcField *fields, int32_t n_fields, const float *co
                        int64_t V, const float *world2rf, const float *blend, const float *exposure,
                        int white_bg, float floater_thresh, int refine, float *rgb, float *depth,
                        float *dirs, int n_threads);
+/* same, plus margin [N] (or NULL): each ray's smallest |w - rayMarch_weight_thres| over the samples of
+ * all active fields (test bookkeeping for exact ties on the hard switch of tensorBase.py:622) */
+void orc_local_forward_m(const OrcField *fields, int32_t n_fields, const float *const *zs,
+                         const int32_t *Ss, const int64_t *ray_ids, int64_t N, int32_t W, int32_t H,
+                         int fov360, float focal, float cx, float cy, const float *cam2world,
+                         int64_t V, const float *world2rf, const float *blend, const float *exposure,
+                         int white_bg, float floater_thresh, int refine, float *rgb, float *depth,
+                         float *dirs, float *margin, int n_threads);
 
 /* Gradients of TensorBase.forward (what torch autograd computes through tensorBase.py:567-636 with
  * floater_thresh = 0): given dL/d(rgb_map) [N][3] and dL/d(depth_map) [N], accumulates dL/d(parameter)

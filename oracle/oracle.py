@@ -94,6 +94,7 @@ def lib():
             C.POINTER(C.c_int64), C.c_int64, C.c_int32, C.c_int32, C.c_int, C.c_float, C.c_float,
             C.c_float, _fp, C.c_int64, _fp, _fp, _fp, C.c_int, C.c_float, C.c_int, _fp, _fp, _fp,
             C.c_int]
+        L.orc_local_forward_m.argtypes = L.orc_local_forward.argtypes[:-1] + [_fp, C.c_int]
         L.orc_field_backward.argtypes = [
             C.POINTER(OrcField), _fp, C.c_int64, _fp, C.c_int32, C.c_int, _fp, _fp,
             C.POINTER(OrcGrads), _fp]
@@ -253,8 +254,10 @@ def ray_directions(ray_ids, W, H, fov360, focal, cx, cy):
 
 
 def local_forward(fields, zs, ray_ids, W, H, fov360, focal, cx, cy, cam2world, world2rf, blend,
-                  exposure=None, white_bg=True, floater_thresh=0.0, refine=False, n_threads=0):
-    """LocalTensorfs.forward restated -> dict(rgb[N,3], depth[N], directions[N,3])"""
+                  exposure=None, white_bg=True, floater_thresh=0.0, refine=False, n_threads=0,
+                  with_margin=False):
+    """LocalTensorfs.forward restated -> dict(rgb[N,3], depth[N], directions[N,3]); with_margin adds
+    margin[N] = each ray's smallest |w - rayMarch_weight_thres| over samples and active fields."""
     n = len(fields)
     arr = (OrcField * n)(*[f.struct for f in fields])
     zs = [_f32(z).reshape(-1) for z in zs]
@@ -269,12 +272,16 @@ def local_forward(fields, zs, ray_ids, W, H, fov360, focal, cx, cy, cam2world, w
     ex = _f32(exposure).reshape(V, 3, 3) if exposure is not None else None
     rgb = np.empty((N, 3), np.float32); depth = np.empty(N, np.float32)
     dirs = np.empty((N, 3), np.float32)
-    lib().orc_local_forward(arr, n, zp, Ss, ids.ctypes.data_as(C.POINTER(C.c_int64)), N, W, H,
-                            int(fov360), float(focal), float(cx), float(cy), _p(c2w), V, _p(w2r),
-                            _p(bl), _p(ex) if ex is not None else None, int(bool(white_bg)),
-                            float(floater_thresh), int(bool(refine)), _p(rgb), _p(depth), _p(dirs),
-                            int(n_threads))
-    return dict(rgb=rgb, depth=depth, directions=dirs)
+    margin = np.empty(N, np.float32) if with_margin else None
+    lib().orc_local_forward_m(arr, n, zp, Ss, ids.ctypes.data_as(C.POINTER(C.c_int64)), N, W, H,
+                              int(fov360), float(focal), float(cx), float(cy), _p(c2w), V, _p(w2r),
+                              _p(bl), _p(ex) if ex is not None else None, int(bool(white_bg)),
+                              float(floater_thresh), int(bool(refine)), _p(rgb), _p(depth), _p(dirs),
+                              _p(margin) if with_margin else None, int(n_threads))
+    out = dict(rgb=rgb, depth=depth, directions=dirs)
+    if with_margin:
+        out["margin"] = margin
+    return out
 
 
 def field_backward(field, fd, rays, z, g_rgb, g_depth, white_bg=True):

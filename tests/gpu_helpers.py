@@ -45,3 +45,36 @@ def local_from_golden(g, device="cuda"):
     sd = {k[3:]: torch.from_numpy(np.asarray(v)) for k, v in g.items() if k.startswith("sd.")}
     lt.load(sd)           # the reference's own checkpoint-restore path (local_tensorfs.py:331-356)
     return lt.to(device)
+
+
+def oracle_fields(lt):
+    """Every field of a (product) LocalTensorfs as an oracle Field (reference layout, numpy)."""
+    from oracle import oracle as orc
+    out = []
+    for rf in lt.tensorfs:
+        fd = {k: v.detach().cpu().numpy() for k, v in rf.state_dict().items()}
+        kw = rf.get_kwargs()
+        for k in ("density_shift", "distance_scale", "rayMarch_weight_thres", "fea_pe", "view_pe",
+                  "featureC", "app_dim", "step_ratio", "fea2denseAct", "gridSize"):
+            fd[k] = kw[k]
+        out.append(orc.Field(fd))
+    return out
+
+
+def oracle_local(lt, fields, ids, view, W, H, world2rf=None, blend=None, floater_thresh=0.0):
+    """LocalTensorfs.forward (eval) through the CPU oracle, with each ray's threshold margin."""
+    from oracle import oracle as orc
+    n = len(fields)
+    zs = [orc.sample_table(f.n_samples()) for f in fields]
+    focal = float(lt.focal(W).detach().cpu())
+    cx, cy = [float(v) for v in lt.center(W, H).detach().cpu()]
+    c2w = lt.get_cam2world(torch.tensor([view])).detach().cpu().numpy()
+    expo = torch.stack(list(lt.exposure))[[view]].detach().cpu().numpy()
+    if world2rf is None:
+        world2rf = torch.stack([w.detach().cpu() for w in lt.world2rf]).numpy()
+    if blend is None:
+        blend = lt.blending_weights.detach().cpu().numpy()[[view]]
+    return orc.local_forward(fields, zs, np.asarray(ids, np.int64), W, H, lt.fov == 360, focal, cx, cy,
+                             c2w, np.asarray(world2rf, np.float32).reshape(n, 3),
+                             np.asarray(blend, np.float32).reshape(1, n), exposure=expo,
+                             floater_thresh=floater_thresh, with_margin=True)

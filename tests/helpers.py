@@ -52,3 +52,36 @@ def rel_err(a, b, floor=1e-3):
 
 def max_abs(a, b):
     return float(np.max(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))))
+
+
+# ---- BASELINE-size parity with the reference's hard switch accounted for ------------------------
+# tensorBase.py:622 shades a sample iff w > rayMarch_weight_thres (1e-3).  alpha = 1 - exp(-x) is
+# quantised to the fp32 spacing below 1.0 (6e-8), so two correct fp32 evaluations of the same ray
+# (ATen's vectorised exp, glibc's, CUDA's -- each within 1 ulp, not bit-identical) can put a weight
+# that is within ~1e-7 of 1e-3 on different sides of the switch; the ray's colour then moves by that
+# sample's w * rgb <= 1e-3.  Such a ray is an exact-threshold TIE, not a parity error: it is accepted
+# only if its smallest |w - thres| (computed by the comparison's reference side) is below TIE_MARGIN
+# and its error is bounded by a couple of flipped samples.
+TIE_MARGIN = 2.5e-7
+TIE_MAX_ERR = 2.5e-3
+
+
+def ray_err(a, b, floor=1e-3):
+    a = np.asarray(a, np.float64).reshape(len(a), -1)
+    b = np.asarray(b, np.float64).reshape(len(b), -1)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor), axis=1)
+
+
+def check_with_ties(out, ref, margin, tol=1e-4, what="", max_tie_frac=0.01):
+    """Every ray within `tol` of the reference, except proven threshold ties.  Returns
+    (n_ties, worst error among the non-tie rays)."""
+    err = ray_err(out, ref)
+    bad = np.nonzero(err > tol)[0]
+    margin = np.asarray(margin, np.float64)
+    unexplained = [(int(r), float(err[r]), float(margin[r])) for r in bad
+                   if not (margin[r] < TIE_MARGIN and err[r] < TIE_MAX_ERR)]
+    assert not unexplained, (f"{what}: {len(unexplained)} rays beyond {tol} that are NOT threshold ties "
+                             f"(ray, err, min|w-thres|): {unexplained[:8]}")
+    assert len(bad) <= max_tie_frac * len(err), f"{what}: {len(bad)} threshold ties of {len(err)} rays"
+    ok = np.ones(len(err), bool); ok[bad] = False
+    return len(bad), float(err[ok].max()) if ok.any() else 0.0
