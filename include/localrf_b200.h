@@ -112,10 +112,26 @@ typedef struct LrfOutputs {
                                  here (r,g,b,depth) instead of to rgb/depth -- the layout the multi-GPU
                                  path all-gathers in one collective */
   unsigned long long *stats;  /* optional [2]: += {density samples marched, appearance samples shaded} */
+  /* ---- fused pixel exchange (multi-GPU): when n_peers > 0 the thread that finishes a
+   * ray on the `finalize` launch ALSO stores its (r,g,b,depth) as one 16-byte word into every
+   * peer_pix[p] + 4*ray -- peer-mapped device memory of the other GPUs (NVLink P2P / symmetric
+   * memory), each pointer already offset to where THIS rank's rays live in that peer's gathered
+   * [total_rays][4] buffer -- so the all-gather of rendered pixels happens inside the render kernel,
+   * store by store, instead of as a collective after it.  `pix` must be set (local copy).  If
+   * mc_pix is set (NVLS multicast mapping of the same buffer) ONE multimem store reaches all peers
+   * and peer_pix is ignored.  lrf_peer_barrier() then closes the step. */
+  int32_t n_peers;            /* 0 = no exchange; <= LRF_MAX_PEERS */
+  float *peer_pix[16];
+  float *mc_pix;
 } LrfOutputs;
+#define LRF_MAX_PEERS 16
 
 int lrf_version(void);
 const char *lrf_last_error(void);
+/* sizeof() of the ABI structs as this library was compiled: 0 LrfField, 1 LrfBatch, 2 LrfOutputs,
+ * 3 LrfGradients (0 for any other index).  Bindings compare these with their own mirrors at load
+ * time, so a stale library or a drifted mirror fails loudly instead of mis-reading arguments. */
+size_t lrf_sizeof(int32_t which);
 
 /* Device bytes of the per-field "prepared" block (folded / re-laid-out MLP weights). */
 size_t lrf_prepared_bytes(void);
@@ -182,6 +198,15 @@ int lrf_render_backward(const LrfField *field, const void *prepared_bwd, const f
                         int64_t n_rays, int32_t white_bg, const float *grad_rgb,
                         const float *grad_depth, const LrfGradients *grads, void *scratch,
                         size_t scratch_bytes, lrf_stream_t stream);
+
+/* Closes a fused pixel exchange: enqueues on `stream` a one-CTA kernel that (1) makes this GPU's
+ * earlier peer stores visible system-wide, (2) writes `seq` into slot `rank` of every peer's flag
+ * array (peer_flags[p] = peer p's [world] uint64 array, peer-mapped; peer_flags[rank] is this GPU's
+ * own), (3) waits until all `world` slots of the local array have reached `seq`.  When the kernel
+ * ends, every rank's pixels of step `seq` are in this GPU's gathered buffer.  `seq` must increase by
+ * one per step, starting at 1 (flags zero-initialised).  replaces: the ncclAllGather of SURVEY.md 8e. */
+int lrf_peer_barrier(unsigned long long *const *peer_flags, int32_t rank, int32_t world,
+                     unsigned long long seq, lrf_stream_t stream);
 
 /* [C][H][W] (contiguous NCHW parameter of the reference) -> [H][W][C] */
 int lrf_repack_nchw_to_nhwc(const float *src, float *dst, int32_t C, int32_t H, int32_t W,

@@ -61,7 +61,8 @@ class LrfBatch(C.Structure):
 
 class LrfOutputs(C.Structure):
     _fields_ = [("rgb", _vp), ("depth", _vp), ("weights", _vp), ("directions", _vp),
-                ("ij", _vp), ("pix", _vp), ("stats", _vp)]
+                ("ij", _vp), ("pix", _vp), ("stats", _vp),
+                ("n_peers", C.c_int32), ("peer_pix", _vp * 16), ("mc_pix", _vp)]
 
 
 class LrfGradients(C.Structure):
@@ -70,11 +71,11 @@ class LrfGradients(C.Structure):
                 ("d_w3", _vp), ("d_b3", _vp)]
 
 
-EXPORTS = ["lrf_version", "lrf_last_error", "lrf_prepared_bytes", "lrf_field_prepare",
+EXPORTS = ["lrf_version", "lrf_sizeof", "lrf_last_error", "lrf_prepared_bytes", "lrf_field_prepare",
            "lrf_render", "lrf_mlp_forward", "lrf_app_products", "lrf_density_feature_backward",
            "lrf_app_products_backward", "lrf_density_feature", "lrf_app_feature", "lrf_repack_nchw_to_nhwc",
            "lrf_launch_info", "lrf_prepared_backward_bytes", "lrf_backward_scratch_bytes",
-           "lrf_field_prepare_backward", "lrf_render_backward"]
+           "lrf_field_prepare_backward", "lrf_render_backward", "lrf_peer_barrier"]
 
 
 def _stale():
@@ -103,8 +104,13 @@ def build(force=False, verbose=False):
 _lib = None
 
 
+ABI_VERSION = 2
+
+
 def lib():
-    """Loads the shared library (building it if sources are newer).  Raises if unavailable."""
+    """Loads the shared library (building it if sources are newer).  Raises if it is missing, if a
+    needed rebuild fails (a stale binary is never loaded silently), or if the binary's ABI version or
+    struct sizes differ from the ctypes mirrors in this file."""
     global _lib
     if _lib is not None:
         return _lib
@@ -112,11 +118,19 @@ def lib():
         try:
             build()
         except (RuntimeError, FileNotFoundError) as e:
-            if not os.path.exists(LIB_PATH):
-                raise RuntimeError(
-                    "localrf_b200: the CUDA library is not built and nvcc failed; there is no "
-                    f"CPU fallback ({e})") from e
+            raise RuntimeError(
+                "localrf_b200: the CUDA library is missing or older than its sources and rebuilding "
+                f"it failed; there is no CPU fallback and no stale binary is loaded ({e})") from e
     L = C.CDLL(LIB_PATH)
+    if not hasattr(L, "lrf_sizeof") or L.lrf_version() != ABI_VERSION:
+        raise RuntimeError(f"localrf_b200: {LIB_PATH} has a different ABI version than this binding; "
+                           "rebuild it (python -c 'import localrf_b200; localrf_b200.build(force=True)')")
+    L.lrf_sizeof.restype = C.c_size_t
+    L.lrf_sizeof.argtypes = [C.c_int32]
+    for which, mirror in enumerate((LrfField, LrfBatch, LrfOutputs, LrfGradients)):
+        if L.lrf_sizeof(which) != C.sizeof(mirror):
+            raise RuntimeError(f"localrf_b200: struct {mirror.__name__} is {L.lrf_sizeof(which)} bytes in "
+                               f"{LIB_PATH} but {C.sizeof(mirror)} in the ctypes mirror -- stale build")
     L.lrf_version.restype = C.c_int
     L.lrf_last_error.restype = C.c_char_p
     L.lrf_prepared_bytes.restype = C.c_size_t
@@ -136,6 +150,7 @@ def lib():
     L.lrf_field_prepare_backward.argtypes = [C.POINTER(LrfField), _vp, _vp]
     L.lrf_render_backward.argtypes = [C.POINTER(LrfField), _vp, _vp, C.c_int64, C.c_int32, _vp, _vp,
                                       C.POINTER(LrfGradients), _vp, C.c_size_t, _vp]
+    L.lrf_peer_barrier.argtypes = [C.POINTER(_vp), C.c_int32, C.c_int32, C.c_uint64, _vp]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError if the header and the library ever drift apart
     _lib = L

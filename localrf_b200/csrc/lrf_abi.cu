@@ -22,6 +22,8 @@ cudaError_t launch_density_feature(const FieldDev& F, const float* xyz, long lon
 cudaError_t launch_app_feature(const FieldDev& F, const float* basis, const float* xyz,
                                long long M, float* out, cudaStream_t stream);
 cudaError_t launch_repack(const float* src, float* dst, int C, long long HW, cudaStream_t stream);
+cudaError_t launch_peer_barrier(unsigned long long* const* peer_flags, int rank, int world,
+                                unsigned long long seq, cudaStream_t stream);
 cudaError_t launch_app_products(const FieldDev& F, const float* xyz, long long M, float* out,
                                 cudaStream_t stream);
 cudaError_t launch_density_backward(const FieldDev& F, float* const* d_plane, float* const* d_line,
@@ -144,7 +146,17 @@ int make_field(const LrfField* f, bool need_mlp, bool need_table, const void* pr
 
 extern "C" {
 
-int lrf_version(void) { return 1; }
+int lrf_version(void) { return 2; }
+
+size_t lrf_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(LrfField);
+    case 1: return sizeof(LrfBatch);
+    case 2: return sizeof(LrfOutputs);
+    case 3: return sizeof(LrfGradients);
+    default: return 0;
+  }
+}
 
 const char* lrf_last_error(void) { return g_err; }
 
@@ -212,6 +224,22 @@ int lrf_render(const LrfField* f, const void* prepared, const LrfBatch* b, const
   B.dirs = b->rays ? nullptr : o->directions;
   B.ij = b->rays ? nullptr : reinterpret_cast<long long*>(o->ij);
   B.stats = o->stats;
+  if (o->n_peers < 0 || o->n_peers > LRF_MAX_PEERS) return fail(LRF_ERR_INVALID, "n_peers out of range");
+  B.n_peers = o->n_peers;
+  B.mc_pix = nullptr;
+  if (o->n_peers > 0) {
+    if (!o->pix) return fail(LRF_ERR_INVALID, "the fused pixel exchange needs the interleaved `pix` output");
+    if (o->mc_pix) {
+      if ((uintptr_t)o->mc_pix & 15) return fail(LRF_ERR_INVALID, "mc_pix must be 16-byte aligned");
+      B.mc_pix = o->mc_pix;
+    } else {
+      for (int p = 0; p < o->n_peers; ++p) {
+        if (!o->peer_pix[p] || ((uintptr_t)o->peer_pix[p] & 15))
+          return fail(LRF_ERR_INVALID, "peer_pix pointers must be non-NULL and 16-byte aligned");
+        B.peer_pix[p] = o->peer_pix[p];
+      }
+    }
+  }
   DevInfo d;
   rc = device_info(d);
   if (rc != LRF_OK) return rc;
@@ -360,6 +388,18 @@ int lrf_render_backward(const LrfField* f, const void* prepared_bwd, const float
                                                   static_cast<const float*>(prepared_bwd), *g, scratch,
                                                   d.n_sms, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "render_backward");
+  return LRF_OK;
+}
+
+int lrf_peer_barrier(unsigned long long* const* peer_flags, int32_t rank, int32_t world,
+                     unsigned long long seq, lrf_stream_t stream) {
+  if (!peer_flags || world < 1 || world > LRF_MAX_PEERS || rank < 0 || rank >= world)
+    return fail(LRF_ERR_INVALID, "bad peer_flags / rank / world");
+  for (int p = 0; p < world; ++p)
+    if (!peer_flags[p] || ((uintptr_t)peer_flags[p] & 7))
+      return fail(LRF_ERR_INVALID, "peer flag arrays must be non-NULL and 8-byte aligned");
+  cudaError_t e = lrf::launch_peer_barrier(peer_flags, rank, world, seq, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "peer_barrier_kernel");
   return LRF_OK;
 }
 

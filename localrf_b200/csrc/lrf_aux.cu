@@ -321,4 +321,31 @@ cudaError_t launch_repack(const float* src, float* dst, int C, long long HW, cud
   return cudaGetLastError();
 }
 
+// ---- fused pixel exchange: step barrier over peer-mapped flags (include/localrf_b200.h) ----------
+struct PeerFlags { unsigned long long* p[16]; };
+
+__global__ void peer_barrier_kernel(const PeerFlags F, const int rank, const int world,
+                                    const unsigned long long seq) {
+  const int t = threadIdx.x;
+  if (t >= world) return;
+  // the render kernel before us on this stream stored pixels into the peers' buffers: order those
+  // stores before the flag for every observer in the system
+  __threadfence_system();
+  unsigned long long* remote = F.p[t] + rank;          // my slot in peer t's flag array
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(seq) : "memory");
+  const unsigned long long* local = F.p[rank] + t;     // peer t's slot in my flag array
+  unsigned long long v = 0;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(local) : "memory");
+  } while (v < seq);
+}
+
+cudaError_t launch_peer_barrier(unsigned long long* const* peer_flags, int rank, int world,
+                                unsigned long long seq, cudaStream_t stream) {
+  PeerFlags F;
+  for (int p = 0; p < 16; ++p) F.p[p] = p < world ? peer_flags[p] : nullptr;
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(F, rank, world, seq);
+  return cudaGetLastError();
+}
+
 }  // namespace lrf

@@ -83,6 +83,9 @@ struct BatchDev {
   long long* ij;
   unsigned long long* stats;
   unsigned long long* sched;   // ray counter of this launch (library-owned, zeroed per launch)
+  int n_peers;                 // fused pixel exchange: peers that receive this rank's pixels
+  float* peer_pix[16];
+  float* mc_pix;               // NVLS multicast address (one multimem store reaches every peer)
 };
 
 // ---- sampling helpers -------------------------------------------------------------------------

@@ -55,6 +55,7 @@ struct Slot {                       // one ray in flight between a producer and 
   float blend;
   unsigned int rgb[3];              // sum of w * rgb, fixed point
   float acc;
+  float depth;                      // final depth of the ray (for the fused pixel exchange)
   long long ray;
   int pending;                      // 1 (open token) + rows submitted and not yet composited
   int state;                        // 0 free, 1 active
@@ -100,7 +101,8 @@ __host__ __device__ inline SmemV3 smem_v3(int S, bool floater, int nprod) {
 
 // ---- outputs (local_tensorfs.py:467-497) --------------------------------------------------------
 __device__ __forceinline__ void write_rgb(const BatchDev& B, long long r,
-                                          const unsigned int* rgb_fix, float acc, float blend) {
+                                          const unsigned int* rgb_fix, float acc, float blend,
+                                          float depth) {
   float c[3];
   const float bg = B.white_bg ? (1.0f - acc) : 0.0f;              // tensorBase.py:633-634
 #pragma unroll
@@ -126,10 +128,21 @@ __device__ __forceinline__ void write_rgb(const BatchDev& B, long long r,
   }
   float* o = B.rgb + B.rgb_stride * r;
   o[0] = c[0]; o[1] = c[1]; o[2] = c[2];
+  if (B.n_peers > 0 && B.finalize) {
+    // fused pixel exchange: this ray's (r,g,b,depth) goes straight into every peer's gathered buffer
+    if (B.mc_pix) {
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(B.mc_pix + 4 * r),
+                   "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(depth)
+                   : "memory");
+    } else {
+      const float4 v = make_float4(c[0], c[1], c[2], depth);
+      for (int p = 0; p < B.n_peers; ++p) *reinterpret_cast<float4*>(B.peer_pix[p] + 4 * r) = v;
+    }
+  }
 }
 
 __device__ __forceinline__ void finalize_slot(const BatchDev& B, Slot* s) {
-  write_rgb(B, s->ray, s->rgb, s->acc, s->blend);
+  write_rgb(B, s->ray, s->rgb, s->acc, s->blend, s->depth);
   __threadfence_block();
   *reinterpret_cast<volatile int*>(&s->state) = 0;
 }
@@ -427,6 +440,7 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
         if (B.accumulate) dpt = B.depth[B.depth_stride * ray] + dpt;
         B.depth[B.depth_stride * ray] = dpt;
         slot->acc = acc;
+        slot->depth = dpt;
         __threadfence_block();
         const int old = atomicSub(&slot->pending, 1);                  // drop the open token
         if (old == 1) { __threadfence_block(); finalize_slot(B, slot); }

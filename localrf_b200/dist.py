@@ -5,8 +5,18 @@ a contiguous shard of the batch's rays and ONE all-gather of the rendered [rays,
 (rgb + depth) closes the step.  No collective touches the data path itself.  The reference has no
 distributed code at all (its only multi-GPU mode is one scene per process, scripts/train_all.sh).
 
-Backend: NCCL over NVLink 5 / NVSwitch on GPUs, gloo in the CPU tests of this host logic.
+Two ways to close a step:
+
+  * `PixelExchange` (the B200 path): the gathered [rays, 4] buffer lives in symmetric memory
+    (peer-mapped over NVLink / NVSwitch); the thread of the render kernel that finishes a ray stores
+    its (r,g,b,depth) straight into every peer's copy -- one 16-byte store per peer, or one NVLS
+    multimem store for all of them -- and `lrf_peer_barrier` (a one-CTA kernel over peer-mapped
+    flags) closes the step.  The all-gather IS the kernel's epilogue; no collective is launched.
+  * `gather_pixels`: one NCCL all-gather (fallback when peer access is unavailable; gloo in the CPU
+    tests of this host logic).
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -55,12 +65,78 @@ def gather_pixels(rgb, depth, n_total, group=None):
     return full[:, :3].contiguous(), full[:, 3].contiguous()
 
 
-def render_sharded(local_tensorfs, ray_ids, view_ids, W, H, group=None, **kw):
+class PixelExchange:
+    """Gathered pixel buffer in symmetric memory + the step barrier (fused pixel exchange).
+
+    Two [max_rays, 4] buffers alternate between steps: a rank may already be storing step i+1 into its
+    peers while they still read step i; it cannot reach step i+2 before every peer has passed the
+    barrier of step i+1, which in the peer's stream order comes after its reads of step i.
+    """
+    FLAG_BYTES = 16 * 8
+
+    def __init__(self, max_rays, group=None, device=None, use_multicast=True):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 16:
+            raise ValueError("PixelExchange covers the GPUs of one node (<= 16 peers)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.max_rays = int(max_rays)
+        self.buf_bytes = (self.max_rays * 16 + 255) // 256 * 256
+        total = 2 * self.buf_bytes + self.FLAG_BYTES
+        self.mem = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
+        self.mem.zero_()
+        torch.cuda.synchronize(self.device)
+        self.handle = symm_mem.rendezvous(self.mem, self.group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        mc = 0
+        if use_multicast:
+            try:
+                mc = int(self.handle.multicast_ptr) if self.handle.has_multicast_support(
+                    self.device.type, self.device.index) else 0
+            except Exception:
+                mc = 0
+        self.mc_ptr = mc
+        self.seq = 0
+        self._flag_ptrs = (C.c_void_p * self.world)(*[p + 2 * self.buf_bytes for p in self.ptrs])
+        self._lib = _lib
+        dist.barrier(self.group)          # every rank has zeroed + mapped before anybody stores
+
+    def fill_outputs(self, o, ray_lo):
+        """Points an LrfOutputs at the NEXT step's buffer: peer p receives this rank's rays at row
+        `ray_lo` of its gathered buffer."""
+        off = ((self.seq + 1) & 1) * self.buf_bytes + ray_lo * 16
+        o.n_peers = self.world
+        for p in range(self.world):
+            o.peer_pix[p] = self.ptrs[p] + off
+        o.mc_pix = (self.mc_ptr + off) if self.mc_ptr else None
+
+    def close_step(self, stream):
+        """Enqueues the barrier; afterwards `gathered(n)` holds every rank's pixels of this step."""
+        self.seq += 1
+        self._lib.check(self._lib.lib().lrf_peer_barrier(self._flag_ptrs, self.rank, self.world,
+                                                         self.seq, stream))
+
+    def gathered(self, n_rays):
+        off = (self.seq & 1) * self.buf_bytes
+        return self.mem[off:off + n_rays * 16].view(torch.float32).view(n_rays, 4)
+
+
+def render_sharded(local_tensorfs, ray_ids, view_ids, W, H, group=None, exchange=None, **kw):
     """LocalTensorfs.forward with the rays of an eval batch (single view) sharded over the ranks;
-    every rank returns the full (rgb, depth)."""
+    every rank returns the full (rgb, depth).  With a `PixelExchange` the pixels are exchanged by the
+    render kernel itself (returned tensors are views of the exchange buffer, valid until the step
+    after next); without one, by one NCCL all-gather."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     n = ray_ids.shape[0]
     lo, hi = shard_bounds(n, rank, world)
-    rgb, depth, _, _ = local_tensorfs(ray_ids[lo:hi], view_ids, W, H, **kw)
-    return gather_pixels(rgb, depth, n, group)
+    if exchange is None:
+        rgb, depth, _, _ = local_tensorfs(ray_ids[lo:hi], view_ids, W, H, **kw)
+        return gather_pixels(rgb, depth, n, group)
+    if n > exchange.max_rays:
+        raise ValueError(f"batch of {n} rays exceeds the exchange buffer ({exchange.max_rays})")
+    local_tensorfs(ray_ids[lo:hi], view_ids, W, H, exchange=(exchange, lo), **kw)
+    full = exchange.gathered(n)
+    return full[:, :3], full[:, 3]

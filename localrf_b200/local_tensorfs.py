@@ -34,6 +34,39 @@ def ids2pixel(W, H, ids):
     return ids % W, (ids // W) % H
 
 
+class _EvalPlan:
+    """Everything an eval-mode `LocalTensorfs.forward` call derives from the module state, resolved
+    once: active fields, per-launch LrfBatch structs, the device copies of cameras / intrinsics /
+    exposure / blending rows.  A repeated call (the renderer's per-frame or per-batch loop) then only
+    re-checks the guards, allocates outputs and enqueues the launches.
+
+    `guards` = (container, index, tensor, version): the plan is valid while every guarded slot still
+    holds the same tensor object at the same version (optimiser steps, load_state_dict, append_* all
+    bump one of them).  Field parameters are guarded by TensorBase.field_and_prepared's own memo."""
+    __slots__ = ("guards", "launches", "keep", "n", "dev", "out_struct", "key_refs")
+
+    def valid(self):
+        for cont, idx, t, ver in self.guards:
+            cur = cont[idx]
+            if ver == "eq":                          # plain value (e.g. nSamples)
+                if cur != t:
+                    return False
+            elif cur is not t or (ver is not None and t._version != ver):
+                return False
+        return True
+
+
+def _uva_pointer(t):
+    """Device-usable address of a tensor the kernel may touch directly: CUDA memory, or PINNED host
+    memory (zero-copy over PCIe: under unified addressing the device address equals the host one)."""
+    if t.is_cuda:
+        return t.data_ptr()
+    if not t.is_pinned():
+        raise RuntimeError("localrf_b200: host tensors handed to the render path must be pinned "
+                           "(page-locked) memory; pageable memory is not device-accessible")
+    return t.data_ptr()
+
+
 class LocalTensorfs(torch.nn.Module):
     """Self-calibrating sequence of local radiance fields."""
 
@@ -388,10 +421,106 @@ class LocalTensorfs(torch.nn.Module):
 
     def forward(self, ray_ids, view_ids, W, H, white_bg=True, is_train=True, cam2world=None,
                 world2rf=None, blending_weights=None, chunk=16384, test_id=False,
-                floater_thresh=0, stats=None):
-        """-> (rgbs [N,3], depth_maps [N], directions [N,3], ij [N,2]) like the reference."""
-        _require_cuda(ray_ids, "ray_ids")
-        dev = ray_ids.device
+                floater_thresh=0, stats=None, exchange=None, out=None):
+        """-> (rgbs [N,3], depth_maps [N], directions [N,3], ij [N,2]) like the reference.
+
+        Extensions (all optional, defaults = the reference's behaviour):
+        `ray_ids` may be a PINNED host tensor: the kernel reads the ids over PCIe itself (no staging
+        copy).  `out=(rgb [N,3], depth [N])` preallocated float32 outputs, on the device or in pinned
+        host memory -- in the latter case finished pixels are stored straight into host memory by the
+        kernel and only a stream synchronisation is left to the caller.
+        `exchange=(PixelExchange, ray_lo)` (multi-GPU eval, dist.render_sharded): the kernel also
+        stores every finished pixel into all peers' gathered buffers at row ray_lo + r and the step
+        barrier is enqueued after the last launch; rgbs / depth_maps are then views of an interleaved
+        [N,4] buffer."""
+        if ray_ids.is_cuda:
+            dev = ray_ids.device
+        else:
+            _uva_pointer(ray_ids)                       # raises unless pinned
+            dev = self.blending_weights.device
+            if dev.type != "cuda":
+                raise RuntimeError("localrf_b200: the scene model is on the CPU; the render path runs "
+                                   "only on a CUDA device (there is no CPU fallback)")
+        n = ray_ids.shape[0]
+        if not is_train and not torch.is_grad_enabled():
+            # eval fast path: reuse the resolved plan of an identical earlier call
+            vkey = (id(view_ids), view_ids._version) if torch.is_tensor(view_ids) else tuple(view_ids)
+            key = (vkey, n, W, H, bool(white_bg), bool(test_id), float(floater_thresh),
+                   None if cam2world is None else (id(cam2world), cam2world._version),
+                   None if world2rf is None else id(world2rf),
+                   None if blending_weights is None else (id(blending_weights), blending_weights._version),
+                   id(self.blending_weights), len(self.tensorfs), exchange is not None, dev)
+            plans = self.__dict__.setdefault("_plans", {})
+            plan = plans.get(key)
+            if plan is not None and plan.valid():
+                return self._run_plan(plan, ray_ids, stats, exchange, out)
+            res = self._forward_general(ray_ids, view_ids, W, H, white_bg, is_train, cam2world, world2rf,
+                                        blending_weights, chunk, test_id, floater_thresh, stats, exchange,
+                                        out, dev, want_plan=True)
+            if isinstance(res, tuple) and len(res) == 2 and isinstance(res[0], _EvalPlan):
+                plan, res = res
+                # the key holds ids of caller objects: keep them alive so the ids cannot be recycled
+                plan.key_refs = (view_ids, cam2world, world2rf, blending_weights)
+                if len(plans) >= 64:
+                    plans.clear()
+                plans[key] = plan
+            return res
+        return self._forward_general(ray_ids, view_ids, W, H, white_bg, is_train, cam2world, world2rf,
+                                     blending_weights, chunk, test_id, floater_thresh, stats, exchange,
+                                     out, dev, want_plan=False)
+
+    def _alloc_outputs(self, n, dev, exchange, out):
+        """(pix or None, rgbs, depth, directions, ij) -- fresh tensors owned by the caller."""
+        pix = None
+        if exchange is not None:
+            pix = torch.empty(n, 4, dtype=torch.float32, device=dev)
+            rgbs, depth = pix[:, :3], pix[:, 3]
+        elif out is not None:
+            rgbs, depth = out
+            for t, shape in ((rgbs, (n, 3)), (depth, (n,))):
+                if t.dtype != torch.float32 or tuple(t.shape) != shape or not t.is_contiguous():
+                    raise ValueError("out=(rgb [N,3], depth [N]) must be contiguous float32 tensors")
+                _uva_pointer(t)
+        else:
+            rgbs = torch.empty(n, 3, dtype=torch.float32, device=dev)
+            depth = torch.empty(n, dtype=torch.float32, device=dev)
+        directions = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        ij = torch.empty(n, 2, dtype=torch.int64, device=dev)
+        return pix, rgbs, depth, directions, ij
+
+    def _run_plan(self, plan, ray_ids, stats, exchange, out):
+        dev, n = plan.dev, plan.n
+        rays_i = ray_ids
+        if rays_i.dtype != torch.int64 or not rays_i.is_contiguous():
+            rays_i = rays_i.to(torch.int64).contiguous()
+        pix, rgbs, depth, directions, ij = self._alloc_outputs(n, dev, exchange, out)
+        lib = _lib.lib()
+        o = plan.out_struct
+        o.pix = o.rgb = o.depth = None
+        o.n_peers = 0
+        if pix is not None:
+            o.pix = pix.data_ptr()
+        else:
+            o.rgb, o.depth = rgbs.data_ptr(), depth.data_ptr()
+        o.directions, o.ij = directions.data_ptr(), ij.data_ptr()
+        o.stats = stats.data_ptr() if stats is not None else None
+        ids_ptr = rays_i.data_ptr()
+        with torch.cuda.device(dev):
+            stream = _stream(dev)
+            last = len(plan.launches) - 1
+            for pos, (rf, z, b) in enumerate(plan.launches):
+                fs, prep = rf.field_and_prepared(z)
+                b.ray_ids = ids_ptr
+                if pos == last and exchange is not None:
+                    exchange[0].fill_outputs(o, exchange[1])
+                _lib.check(lib.lrf_render(C.byref(fs), _ptr(prep), C.byref(b), C.byref(o), stream))
+            if exchange is not None:
+                exchange[0].close_step(stream)
+        return rgbs, depth, directions, ij
+
+    def _forward_general(self, ray_ids, view_ids, W, H, white_bg, is_train, cam2world, world2rf,
+                         blending_weights, chunk, test_id, floater_thresh, stats, exchange, out, dev,
+                         want_plan):
         n = ray_ids.shape[0]
         # (not memoised: a new tensor can reuse a freed tensor's id and storage)
         ids = view_ids.tolist() if torch.is_tensor(view_ids) else [int(v) for v in view_ids]
@@ -399,6 +528,7 @@ class LocalTensorfs(torch.nn.Module):
         if n_views == 0 or n % n_views != 0:
             raise ValueError("ray_ids must hold the same number of rays for every view")
         n_fields = len(self.tensorfs)
+        guards = []
 
         # -- which fields render, with which per-view weights (:403-418) ----------------------------
         blend = None                                   # device [V, n_fields] or None (= weight 1)
@@ -432,16 +562,28 @@ class LocalTensorfs(torch.nn.Module):
         else:
             needs_composed = False
         if needs_composed or not all(self.tensorfs[k].fused_supported() for k in active):
+            if exchange is not None or out is not None:
+                raise NotImplementedError("exchange= / out= are served by the fused eval path only")
+            if not ray_ids.is_cuda:
+                ray_ids = ray_ids.to(dev)
             return self._forward_autograd(ray_ids, view_ids, ids, W, H, white_bg, is_train,
                                           cam2world, world2rf, blend, active, chunk, test_id,
                                           floater_thresh)
+        if exchange is not None and is_train:
+            raise ValueError("the fused pixel exchange serves eval batches (is_train=False)")
 
         # -- cameras, intrinsics, exposure (memoised on parameter versions) ---------------------------
+        P = self._parameters
+        if blending_weights is None and not is_train:
+            guards.append((P, "blending_weights", self.blending_weights, self.blending_weights._version))
         if cam2world is None:
             src = [self.r_c2w[i] for i in ids] + [self.t_c2w[i] for i in ids]
             key = (tuple(ids), tuple((id(t), t._version) for t in src), str(dev))
             cam2world = self._cached("c2w", key, lambda: self.get_cam2world(ids).detach()
                                      .to(dev, torch.float32).contiguous(), refs=src)
+            for i in set(ids):
+                guards.append((self.r_c2w, i, self.r_c2w[i], self.r_c2w[i]._version))
+                guards.append((self.t_c2w, i, self.t_c2w[i], self.t_c2w[i]._version))
         else:
             cam2world = cam2world.detach().to(dev, torch.float32).contiguous()
         fov360 = self.fov == 360
@@ -450,6 +592,8 @@ class LocalTensorfs(torch.nn.Module):
         intr = self._cached("intr", key, lambda: torch.cat(
             [self.focal(W).detach().reshape(1), self.center(W, H).detach().reshape(2)])
             .to(dev, torch.float32).contiguous(), refs=src)
+        for name in ("init_focal", "focal_offset", "center_rel"):
+            guards.append((P, name, P[name], P[name]._version))
         exposure = None
         if self.lr_exposure_init > 0:
             n_e = len(self.exposure)
@@ -458,14 +602,14 @@ class LocalTensorfs(torch.nn.Module):
             src = [self.exposure[i] for i in used]
             key = (tuple(ids), bool(test_id), n_e, tuple((id(t), t._version) for t in src), str(dev))
             exposure = self._cached("expo", key, lambda: self._exposure_for(ids, test_id, dev), refs=src)
+            for i, t in zip(used, src):
+                guards.append((self.exposure, i, t, t._version))
         rays_i = ray_ids.detach()
         if rays_i.dtype != torch.int64 or not rays_i.is_contiguous():
             rays_i = rays_i.to(torch.int64).contiguous()
+        ids_ptr = _uva_pointer(rays_i)
 
-        rgbs = torch.empty(n, 3, dtype=torch.float32, device=dev)
-        depth = torch.empty(n, dtype=torch.float32, device=dev)
-        directions = torch.empty(n, 3, dtype=torch.float32, device=dev)
-        ij = torch.empty(n, 2, dtype=torch.int64, device=dev)
+        pix, rgbs, depth, directions, ij = self._alloc_outputs(n, dev, exchange, out)
 
         # train mode: the reference draws fresh jitter per chunk; eval has no randomness, so the
         # whole batch is one launch per field.  Chunks are kept on view boundaries (the kernel
@@ -477,6 +621,7 @@ class LocalTensorfs(torch.nn.Module):
         else:
             chunk = n
         lib = _lib.lib()
+        launches, keep = [], [cam2world, intr, exposure, blend]
         with torch.cuda.device(dev):
             stream = _stream(dev)
             for lo in range(0, n, chunk):
@@ -494,7 +639,7 @@ class LocalTensorfs(torch.nn.Module):
                         w2.detach().to(dev, torch.float32).contiguous()
                     b = _lib.LrfBatch()
                     b.n_rays = hi - lo
-                    b.ray_ids = rays_i.data_ptr() + 8 * lo
+                    b.ray_ids = ids_ptr + 8 * lo
                     b.W, b.H = int(W), int(H)
                     b.fov360 = int(fov360)
                     b.intrinsics = intr.data_ptr()
@@ -511,11 +656,30 @@ class LocalTensorfs(torch.nn.Module):
                     b.white_bg = int(bool(white_bg) or bool(is_train and torch.rand((1,)) < 0.5))
                     b.floater_thresh = float(floater_thresh)
                     o = _lib.LrfOutputs()
-                    o.rgb = rgbs.data_ptr() + 12 * lo
-                    o.depth = depth.data_ptr() + 4 * lo
+                    if pix is not None:
+                        o.pix = pix.data_ptr() + 16 * lo
+                        if pos == len(active) - 1:
+                            exchange[0].fill_outputs(o, exchange[1] + lo)
+                    else:
+                        o.rgb = _uva_pointer(rgbs) + 12 * lo
+                        o.depth = _uva_pointer(depth) + 4 * lo
                     o.directions = directions.data_ptr() + 12 * lo
                     o.ij = ij.data_ptr() + 16 * lo
                     if stats is not None:
                         o.stats = stats.data_ptr()
                     _lib.check(lib.lrf_render(C.byref(fs), _ptr(prep), C.byref(b), C.byref(o), stream))
-        return rgbs, depth, directions, ij
+                    if want_plan:
+                        launches.append((rf, z, b))
+                        keep.append(w2rf)
+                        guards.append((self.tensorfs, k, rf, None))
+                        guards.append((world2rf, k, w2, w2._version))
+                        guards.append((rf.__dict__, "nSamples", rf.nSamples, "eq"))
+            if exchange is not None:
+                exchange[0].close_step(stream)
+        result = (rgbs, depth, directions, ij)
+        if want_plan and chunk == n:
+            plan = _EvalPlan()
+            plan.guards, plan.launches, plan.keep = guards, launches, keep
+            plan.n, plan.dev, plan.out_struct, plan.key_refs = n, dev, _lib.LrfOutputs(), None
+            return plan, result
+        return result

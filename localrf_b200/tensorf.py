@@ -97,6 +97,12 @@ class _RenderFn(torch.autograd.Function):
         rays_c = rays.detach().to(torch.float32).contiguous()
         rgb, depth = module._render_fused(rays_c, z, white_bg, 0.0, False, None)
         ctx.module, ctx.white_bg = module, white_bg
+        # the backward re-reads the module's live parameters (nothing per-sample is saved): remember
+        # what the forward saw, so an in-place update / upsample / mask rebuild in between raises like
+        # torch's own version-counter check would instead of producing gradients of a different model
+        am = module.alphaMask
+        ctx.seen = (tuple((p.data_ptr(), p._version) for p in params), tuple(module._grid_host),
+                    None if am is None else (am.alpha_volume.data_ptr(), am.alpha_volume._version))
         ctx.save_for_backward(rays_c, z)
         return rgb, depth
 
@@ -104,6 +110,14 @@ class _RenderFn(torch.autograd.Function):
     def backward(ctx, g_rgb, g_depth):
         rays, z = ctx.saved_tensors
         m, dev, n = ctx.module, rays.device, rays.shape[0]
+        am = m.alphaMask
+        now = (tuple((p.data_ptr(), p._version) for p in m._grad_params()), tuple(m._grid_host),
+               None if am is None else (am.alpha_volume.data_ptr(), am.alpha_volume._version))
+        if now != ctx.seen:
+            raise RuntimeError("localrf_b200: a parameter (or the grid size / alpha mask) of the field was "
+                               "modified between the fused forward and its backward; the backward "
+                               "recomputes from the live parameters and would return gradients of a "
+                               "different model")
         g_rgb = torch.zeros(n, 3, device=dev) if g_rgb is None else g_rgb.detach().to(torch.float32).contiguous()
         g_depth = torch.zeros(n, device=dev) if g_depth is None else g_depth.detach().to(torch.float32).contiguous()
         rm = m.renderModule
@@ -341,13 +355,14 @@ class TensorBase(torch.nn.Module):
                                 ("aplane", self.app_plane), ("aline", self.app_line)):
                 p = plist[i]
                 _require_cuda(p, f"{name}[{i}]")
-                t = p.detach()
-                if t.dtype != torch.float32:
-                    raise TypeError(f"{name}[{i}] must be float32, got {t.dtype}")
-                if not t.is_contiguous(memory_format=torch.channels_last):
-                    t = _cl(t)      # e.g. a parameter swapped in from outside in NCHW layout
-                    keep.append(t)
-                getattr(s, name)[i] = t.data_ptr()
+                if p.dtype != torch.float32:
+                    raise TypeError(f"{name}[{i}] must be float32, got {p.dtype}")
+                if not p.is_contiguous(memory_format=torch.channels_last):
+                    # a parameter swapped in from outside in NCHW layout: re-lay it out IN PLACE, once,
+                    # so the struct always points at the live storage the optimiser updates (a
+                    # temporary copy would go stale on the next in-place update)
+                    p.data = _cl(p.data)
+                getattr(s, name)[i] = p.data_ptr()
         s.app_dim = self.app_dim
         s.featureC = self.featureC
         s.fea_pe, s.view_pe = self.fea_pe, self.view_pe
@@ -358,17 +373,18 @@ class TensorBase(torch.nn.Module):
                             ("b2", rm.mlp[2].bias), ("w3", rm.mlp_view[0].weight),
                             ("b3", rm.mlp_view[0].bias)):
                 _require_cuda(t, name)
-                t = t.detach()
+                if t.dtype != torch.float32:
+                    raise TypeError(f"{name} must be float32, got {t.dtype}")
                 if not t.is_contiguous():
-                    t = t.contiguous(); keep.append(t)
+                    t.data = t.data.contiguous()       # in place, for the same reason as above
                 setattr(s, name, t.data_ptr())
         else:
             s.basis = self.basis_mat.weight.detach().data_ptr()
         if self.alphaMask is not None:
-            vol = self.alphaMask.alpha_volume.detach()
+            vol = self.alphaMask.alpha_volume
             _require_cuda(vol, "alphaMask.alpha_volume")
-            vol = vol.contiguous()
-            keep.append(vol)
+            if vol.dtype != torch.float32 or not vol.is_contiguous():
+                vol.data = vol.data.to(torch.float32).contiguous()     # the kernel reads fp32 [D][H][W]
             s.alpha_vol = vol.data_ptr()
             for i in range(3):
                 s.alpha_dims[i] = vol.shape[-3 + i]

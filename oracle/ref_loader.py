@@ -1,8 +1,9 @@
 """Import the UNMODIFIED reference (facebookresearch/localrf) from /root/reference on CPU.
 
-TEST INFRASTRUCTURE ONLY.  Used by tests/golden/make_golden.py (in the build container, where
-/root/reference is mounted) to produce the committed golden fixtures.  Nothing under localrf_b200/
-imports this file, and nothing that runs on the GPU box may call it (/root/reference is absent there).
+TEST / BENCH INFRASTRUCTURE ONLY.  Used by tests/golden/make_golden.py (in the build container, where
+/root/reference is mounted) to produce the committed golden fixtures, and -- through the staged
+byte-identical copy under baseline/_ref/ (oracle/vendor_ref.py) -- by `bench.py --impl reference` and
+tests/test_gpu_vs_reference.py on the GPU box.  Nothing under localrf_b200/ imports this file.
 
 The hot path's modules import a few packages that are missing from this image but are never
 *used* on the path (kornia.create_meshgrid at utils/ray_utils.py:6, matplotlib / plyfile /
@@ -14,7 +15,21 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("LOCALRF_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """$LOCALRF_REFERENCE, else /root/reference (build container), else the byte-identical staged
+    copy under baseline/_ref/ (oracle/vendor_ref.py; the only one present on the GPU box)."""
+    cands = [os.environ.get("LOCALRF_REFERENCE"), "/root/reference",
+             os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "localTensoRF", "local_tensorfs.py")):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _find_root()
 REF_PKG = os.path.join(REF_ROOT, "localTensoRF")
 
 

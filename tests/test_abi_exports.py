@@ -26,16 +26,21 @@ def test_header_symbols_exported():
 
 def test_version_and_prepared_size():
     L = _lib.lib()
-    assert L.lrf_version() == 1
+    assert L.lrf_version() == _lib.ABI_VERSION
     # bf16 hi+lo images of W1B [128][80] and W2 [128][128], then fp32 b1, b2, W3[3][132], b3[4]
     assert L.lrf_prepared_bytes() == 2 * 2 * (128 * 80 + 128 * 128) + 4 * (128 + 128 + 3 * 132 + 4)
 
 
 def test_struct_sizes_match_c_layout():
     # natural-alignment layouts of the header structs (x86-64)
-    assert C.sizeof(_lib.LrfOutputs) == 7 * 8
+    assert C.sizeof(_lib.LrfOutputs) == 7 * 8 + 8 + 16 * 8 + 8     # + n_peers (padded), peer_pix[16], mc_pix
     assert C.sizeof(_lib.LrfBatch) == 120
     assert C.sizeof(_lib.LrfField) % 8 == 0
+    # ... and the compiled library agrees with every ctypes mirror (checked again at load time)
+    L = _lib.lib()
+    for which, mirror in enumerate((_lib.LrfField, _lib.LrfBatch, _lib.LrfOutputs, _lib.LrfGradients)):
+        assert L.lrf_sizeof(which) == C.sizeof(mirror), mirror.__name__
+    assert L.lrf_sizeof(99) == 0
 
 
 def test_validation_errors_without_gpu():
