@@ -1,27 +1,45 @@
 #!/usr/bin/env python
-"""bench.py -- rays/s of the fused render path at a 300^3 VM grid, 4096-ray batches (BASELINE.json).
+"""bench.py -- rays/s of the fused render path (BASELINE.json: 300^3 VM grid, 4096-ray batches).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cfg2|distB|incoherent|cfg3|cfg5] [--scaling weak|strong|frame]
+                    [--exchange fused|nccl]
 
-Workload: one TensorVMSplit at 300^3 built with the reference's constructor
-defaults and torch.manual_seed(0) ("distribution A", random init), an 800x800 pinhole frame at
-fov 85.6, identity pose, cut into 157 batches of 4096 rays.  One STEP = one 4096-ray batch
-(ray generation + march + shading + composite = one fused launch).  Steps walk through the frame's
-batches, so consecutive steps use different rays.
+Workloads (fields built by the reference's constructor defaults, random init):
+  cfg2        (default, the headline) one TensorVMSplit at 300^3, seed 0, an 800x800 pinhole frame at
+              fov 85.6, identity pose, cut into 4096-ray batches; step = one batch
+  distB       cfg2 with density_shift = +2 ("opaque": early ray termination)
+  incoherent  cfg2's field, training-style batches: 16 views x 256 random pixels each
+  cfg3        three 300^3 fields (seeds 0,1,2), world2rf offsets, explicit blend [0.2,0.5,0.3]
+  cfg5        slice of config 5: 8 fields at 640^3 (S = 738), 64-frame trajectory along -z with the
+              reference's own cross-fade rows, floater_thresh 0.5; step = one 4096-ray batch of a frame
+
+One STEP = one batch through the public API `LocalTensorfs.forward` (one fused launch per active
+field: ray generation + march + shading + composite + blend).  Steps walk through different batches.
 
   value     rays/s with the batch's ray ids already in HBM; each step timed with CUDA events on the
-            launching stream, a 256 MiB write between steps flushes the 126 MB L2.
-  e2e       the same step through the public API (LocalTensorfs.forward) from pinned HOST ray ids,
-            host->device copy, launch, device->host copy of rgb+depth, host sync -- every step.
+            launching stream; 2 x 256 MiB writes between steps flush the 126 MB L2 (and keep the GPU
+            busy while the host prepares the next call, so no host time leaks into the events).
+  e2e       the same step from PINNED HOST ray ids to PINNED HOST rgb+depth: the kernel reads the ids
+            and stores the finished pixels over PCIe itself (zero-copy; every input / output byte
+            crosses the bus inside the timed region), then one stream sync -- every step, wall clock.
   roofline  algorithmic gather bytes (576 B per density sample, 1728 B per shaded sample, 40 B per
             ray; samples counted exactly by the kernel) / event-timed launch duration, against the
-            measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline / --impl reference: the CPU oracle port (oracle/, plain C + OpenMP, all host cores)
-            on a bounded sample of the same workload.
+            measured HBM copy bandwidth in MEASURED_PEAKS.json; `traffic` = DRAM bytes per launch of
+            the committed ncu capture of this workload (profiles/traffic.json), or null.
+  cpu_baseline / --impl reference: the UNMODIFIED PyTorch reference (staged byte-identical under
+            baseline/_ref by oracle/vendor_ref.py) on all host cores, 4096 rays per step; the CPU
+            oracle port (oracle/lrf_oracle.c) only if the reference cannot be imported.
+            `reference_gpu` = the same unmodified reference with device="cuda" on this B200.
 
-N > 1 (torchrun, one rank per GPU): the field is replicated, every rank renders its own 4096-ray
-batch per step (global batch N*4096, weak scaling) and one NCCL all-gather of the rendered
-[4096,4] pixels (rgb+depth) closes the step.
+N > 1 (torchrun, one rank per GPU), field replicated, rays sharded, no data-path collective:
+  --scaling weak    every rank renders its own 4096-ray batch per step (global batch N*4096)
+  --scaling strong  each 4096-ray batch is split N ways (BASELINE config 4 as written)
+  --scaling frame   the 640 000 rays of a frame are split N ways, one exchange per frame
+  The rendered [rays,4] pixels (rgb+depth) are exchanged by the render kernel itself: the thread that
+  finishes a ray stores it into every peer's gathered buffer (symmetric memory over NVLink/NVSwitch,
+  NVLS multicast when available) and a one-CTA flag barrier closes the step (--exchange fused);
+  --exchange nccl uses one ncclAllGather per step instead.
 """
 import argparse
 import json
@@ -42,7 +60,6 @@ IMG_W = IMG_H = 800
 BATCH = 4096
 FOV = 85.6
 FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback
-
 
 _REAL_STDOUT = None
 
@@ -65,25 +82,124 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
-def field_kwargs():
-    return dict(density_n_comp=[8, 8, 8], appearance_n_comp=[24, 24, 24], app_dim=27,
-                shadingMode="MLP_Fea_late_view", near_far=[0.1, 1e3], density_shift=-5,
-                alphaMask_thres=1e-4, distance_scale=25, rayMarch_weight_thres=1e-3, pos_pe=0,
-                view_pe=0, fea_pe=0, featureC=128, step_ratio=0.5, fea2denseAct="softplus")
+def field_kwargs(**over):
+    kw = dict(density_n_comp=[8, 8, 8], appearance_n_comp=[24, 24, 24], app_dim=27,
+              shadingMode="MLP_Fea_late_view", near_far=[0.1, 1e3], density_shift=-5,
+              alphaMask_thres=1e-4, distance_scale=25, rayMarch_weight_thres=1e-3, pos_pe=0,
+              view_pe=0, fea_pe=0, featureC=128, step_ratio=0.5, fea2denseAct="softplus")
+    kw.update(over)
+    return kw
 
 
-def build_scene(device, grid=GRID):
-    """LocalTensorfs with one 300^3 field, reference constructor defaults, seed 0."""
-    import localrf_b200 as L
+def _scene(cls, device, grid, n_init_frames=1, **over):
     torch.manual_seed(0)
     aabb = 2 * torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
-    lt = L.LocalTensorfs(camera_prior=None, fov=FOV, n_init_frames=1, n_overlap=30,
-                         WH=(IMG_W, IMG_H), n_iters_per_frame=600, n_iters_reg=100, lr_R_init=5e-3,
-                         lr_t_init=5e-4, lr_i_init=0, lr_exposure_init=1e-3, rf_lr_init=2e-2,
-                         rf_lr_basis=1e-3, lr_decay_target_ratio=0.1, N_voxel_list={},
-                         update_AlphaMask_list=[], lr_upsample_reset=True, device="cpu",
-                         aabb=aabb, gridSize=[grid] * 3, **field_kwargs())
-    return lt.to(device) if device != "cpu" else lt
+    return cls(camera_prior=None, fov=FOV, n_init_frames=n_init_frames, n_overlap=30,
+               WH=(IMG_W, IMG_H), n_iters_per_frame=600, n_iters_reg=100, lr_R_init=5e-3,
+               lr_t_init=5e-4, lr_i_init=0, lr_exposure_init=1e-3, rf_lr_init=2e-2,
+               rf_lr_basis=1e-3, lr_decay_target_ratio=0.1, N_voxel_list={},
+               update_AlphaMask_list=[], lr_upsample_reset=True, device=device,
+               aabb=aabb.to(device) if device != "cpu" else aabb, gridSize=[grid] * 3,
+               **field_kwargs(**over))
+
+
+def build_scene(device, grid=GRID, **over):
+    """Product LocalTensorfs with one field, reference constructor defaults, seed 0 (built on the CPU
+    so the init draws are the reference's, then moved)."""
+    import localrf_b200 as L
+    lt = _scene(L.LocalTensorfs, "cpu", grid, **over)
+    return lt.to(device) if str(device) != "cpu" else lt
+
+
+# ---- workloads -----------------------------------------------------------------------------------
+class Workload:
+    """Scene construction + the batches of one --workload; the SAME code builds the product's scene and
+    the unmodified reference's (both constructors consume the RNG identically)."""
+
+    def __init__(self, name, grid=None):
+        self.name = name
+        self.grid = grid if grid is not None else (640 if name == "cfg5" else GRID)
+        self.floater = 0.5 if name == "cfg5" else 0.0
+        self.n_frames = {"incoherent": 16, "cfg5": 64}.get(name, 1)
+
+    def build(self, cls, quiet=False):
+        import contextlib, io
+        ctx = contextlib.redirect_stdout(io.StringIO()) if quiet else contextlib.nullcontext()
+        with ctx:
+            return self._build(cls)
+
+    def _build(self, cls):
+        name, grid = self.name, self.grid
+        if name in ("cfg2", "distB"):
+            return _scene(cls, "cpu", grid, **({"density_shift": 2} if name == "distB" else {}))
+        if name == "incoherent":
+            lt = _scene(cls, "cpu", grid, n_init_frames=16)
+            g = torch.Generator().manual_seed(5)
+            with torch.no_grad():                     # 16 nearby, distinct cameras
+                for i in range(16):
+                    lt.r_c2w[i].add_(0.05 * torch.randn(3, 2, generator=g))
+                    lt.t_c2w[i].add_(0.1 * torch.randn(3, generator=g))
+            return lt
+        if name == "cfg3":
+            lt = _scene(cls, "cpu", grid)
+            for k in (1, 2):
+                lt.append_frame()                     # append_rf needs >= 2 frames to cross-fade over
+                torch.manual_seed(k)
+                lt.append_rf(1)
+            return lt
+        if name == "cfg5":
+            # 8 fields, 8 frames per field, camera translating along -z; blending rows and world2rf by
+            # the reference's own append_frame / append_rf bookkeeping (local_tensorfs.py:116-177)
+            lt = _scene(cls, "cpu", grid)
+            for f in range(1, self.n_frames):
+                lt.append_frame()
+                with torch.no_grad():
+                    lt.t_c2w[-1].copy_(torch.tensor([0.0, 0.0, -0.05 * f]))
+                if f % 8 == 0:
+                    torch.manual_seed(f // 8)
+                    lt.append_rf(4)
+            return lt
+        raise ValueError(name)
+
+    def call_kwargs(self, lt, dev):
+        kw = dict(is_train=False, chunk=BATCH)
+        if self.floater:
+            kw["floater_thresh"] = self.floater
+        if self.name == "cfg3":
+            kw["world2rf"] = [torch.zeros(3, device=dev), torch.tensor([-0.3, 0.0, 0.0], device=dev),
+                              torch.tensor([-0.6, 0.0, 0.0], device=dev)]
+            kw["blending_weights"] = torch.tensor([[0.2, 0.5, 0.3]], device=dev)
+        return kw
+
+    def batches(self):
+        """-> (ids [n_batches, BATCH] int64 (host), views: list of host int64 tensors per batch)"""
+        n_full = IMG_W * IMG_H // BATCH
+        frame = torch.arange(n_full * BATCH, dtype=torch.int64).view(n_full, BATCH)
+        if self.name == "incoherent":
+            g = torch.Generator().manual_seed(6)
+            px = torch.randint(0, IMG_W * IMG_H, (64, 16, BATCH // 16), generator=g)
+            ids = (px + torch.arange(16)[None, :, None] * IMG_W * IMG_H).reshape(64, BATCH)
+            return ids, [torch.arange(16)] * 64
+        if self.name == "cfg5":
+            ids, views = [], []
+            for i in range(64):
+                ids.append(frame[(i * 37) % n_full])
+                views.append(torch.tensor([(i * 11) % self.n_frames]))
+            return torch.stack(ids), views
+        return frame, [torch.tensor([0])] * n_full
+
+    def describe(self):
+        return {
+            "cfg2": f"cfg2: TensorVMSplit {self.grid}^3 (reference ctor, seed 0, random init), 800x800 pinhole "
+                    "frame fov 85.6 identity pose, 4096-ray batches; step = one batch, steps walk the frame",
+            "distB": f"distribution B: cfg2 with density_shift=+2 (opaque, early ray termination), {self.grid}^3",
+            "incoherent": f"incoherent: cfg2's {self.grid}^3 field, training-style batches of 16 views x 256 "
+                          "random pixels (localrf_dataset.py:273-315), eval arithmetic",
+            "cfg3": f"cfg3: 3 fields {self.grid}^3 (seeds 0,1,2), world2rf (0,-.3,-.6), blend [0.2,0.5,0.3], "
+                    "4096-ray batches of the 800x800 frame",
+            "cfg5": f"cfg5 slice: 8 fields {self.grid}^3, 64-frame -z trajectory, reference cross-fade rows "
+                    "(1-2 active fields per frame), floater_thresh 0.5, 4096-ray batches of varying frames",
+        }[self.name]
 
 
 def peaks():
@@ -94,6 +210,16 @@ def peaks():
         except Exception:
             pass
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def traffic_for(workload):
+    """DRAM bytes per launch from the committed ncu capture of this workload (profiles/traffic.json,
+    written by profiles/ncu_traffic.py from an `ncu --set full` export), or (None, None)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload]
+        return float(t["dram_bytes_per_launch"]), t["source"]
+    except Exception:
+        return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -154,6 +280,7 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+# ---- CPU / reference legs ------------------------------------------------------------------------
 def frame_ids():
     return torch.arange(IMG_W * IMG_H, dtype=torch.int64)
 
@@ -170,7 +297,7 @@ def oracle_field(lt):
 
 
 def oracle_batch(lt, field, ids, n_threads=None):
-    """One batch through the CPU oracle's LocalTensorfs.forward restatement, on ALL host cores
+    """One cfg2 batch through the CPU oracle's LocalTensorfs.forward restatement, on ALL host cores
     (explicit thread count: torchrun exports OMP_NUM_THREADS=1 to its workers)."""
     if n_threads is None:
         n_threads = os.cpu_count() or 1
@@ -185,88 +312,170 @@ def oracle_batch(lt, field, ids, n_threads=None):
                              exposure=expo, n_threads=n_threads)
 
 
-def cpu_baseline(lt, budget_s=12.0):
-    """Oracle port on the host cores, bounded sample of the same workload."""
+def load_reference_classes():
+    """The unmodified reference's LocalTensorfs (baseline/_ref or /root/reference), or None."""
+    try:
+        from oracle.ref_loader import load_reference, reference_available
+        if not reference_available():
+            return None
+        return load_reference()[2]
+    except Exception as e:  # pragma: no cover
+        print(f"bench: reference import failed ({e}); falling back to the oracle port", file=sys.stderr)
+        return None
+
+
+class ReferenceRunner:
+    """Steps of a workload through the UNMODIFIED reference's own public API (its stock PyTorch path)."""
+
+    def __init__(self, wl, device):
+        cls = load_reference_classes()
+        if cls is None:
+            raise RuntimeError("reference not available")
+        self.wl, self.dev = wl, torch.device(device)
+        lt = wl.build(cls, quiet=True)
+        if self.dev.type == "cuda":
+            # the reference's own device handling: parameters follow .to(), helper tensors follow
+            # the `device` attribute (local_tensorfs.py:59,132)
+            # every field resident on the GPU (the reference parks older fields on the CPU and
+            # shuffles them per frame, local_tensorfs.py:132,432-434,476-479; not reproduced here:
+            # this baseline is the reference's arithmetic at its best)
+            lt = lt.to(self.dev)
+            lt.device = self.dev
+            for rf in lt.tensorfs:
+                rf.to(self.dev)                      # TensorBase.to also retargets rf.device / stepSize
+        self.lt = lt
+        ids, views = wl.batches()
+        self.ids = ids.to(self.dev)
+        self.views = [v.to(self.dev) for v in views]
+        self.kw = wl.call_kwargs(lt, self.dev)
+
+    def step(self, i):
+        import contextlib, io
+        bi = (i * 37) % self.ids.shape[0]
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            out = self.lt(self.ids[bi], self.views[bi], IMG_W, IMG_H, **self.kw)
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
+        return out
+
+
+def time_reference(wl, device, warmup, steps):
+    r = ReferenceRunner(wl, device)
+    for i in range(warmup):
+        r.step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        r.step(warmup + i)
+    dt = time.perf_counter() - t0
+    return BATCH * steps / dt, dt
+
+
+def cpu_baseline(wl, budget_s=20.0):
+    """Reported CPU baseline at N=1: the unmodified reference on all host cores (bounded: 1 warm-up +
+    as many 4096-ray batches as fit ~budget_s, at least 2); oracle port if it cannot be imported."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    try:
+        r = ReferenceRunner(wl, "cpu")
+        t0 = time.perf_counter(); r.step(0); t1 = time.perf_counter() - t0
+        steps = int(min(max(budget_s / max(t1, 1e-3), 2), 16))
+        t0 = time.perf_counter()
+        for i in range(steps):
+            r.step(1 + i)
+        dt = time.perf_counter() - t0
+        return {"value": BATCH * steps / dt, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "reference",
+                "sample": f"{steps} batches of 4096 rays of workload {wl.name}, unmodified PyTorch reference "
+                          f"(baseline/_ref, LocalTensorfs.forward, torch {torch.__version__}, "
+                          f"{torch.get_num_threads()} threads), {dt:.2f} s"}
+    except Exception as e:
+        print(f"bench: reference CPU baseline unavailable ({e}); using the oracle port", file=sys.stderr)
+    if wl.name not in ("cfg2", "distB"):
+        return None
+    lt = wl.build(__import__("localrf_b200").LocalTensorfs, quiet=True)
     field = oracle_field(lt)
     ids = frame_ids().numpy()
-    mid = (IMG_W * IMG_H // 2 // BATCH) * BATCH          # a batch from the middle of the frame
-    oracle_batch(lt, field, ids[mid:mid + 256])          # warm-up (page-in, thread pool)
+    mid = (IMG_W * IMG_H // 2 // BATCH) * BATCH
+    oracle_batch(lt, field, ids[mid:mid + 256])
     t0 = time.perf_counter()
-    oracle_batch(lt, field, ids[mid:mid + 1024])
-    t1 = time.perf_counter() - t0
-    n = int(min(max(1024 * budget_s / max(t1, 1e-6), 1024), 16 * BATCH))
-    n = (n // 1024) * 1024
-    t0 = time.perf_counter()
-    oracle_batch(lt, field, ids[mid:mid + n])
+    oracle_batch(lt, field, ids[mid:mid + BATCH])
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{n} consecutive rays of the 800x800 frame (from ray {mid}), oracle/lrf_oracle.c "
-                      f"with OpenMP over {os.cpu_count()} host threads, {dt:.2f} s"}
+    return {"value": BATCH / dt, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"one 4096-ray batch (from ray {mid}), oracle/lrf_oracle.c, OpenMP {os.cpu_count()} threads, {dt:.2f} s"}
 
 
 def run_reference(args):
-    """--impl reference: the CPU oracle port on this box's host cores (rank 0 only)."""
+    """--impl reference: the unmodified PyTorch reference on this box's host cores (rank 0 only),
+    4096 rays per step, same workload / metric as our arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    lt = build_scene("cpu")
-    field = oracle_field(lt)
-    ids = frame_ids().numpy()
-    t0 = time.perf_counter()
-    oracle_batch(lt, field, ids[:256])
-    oracle_batch(lt, field, ids[320000:320512])
-    rate = 512 / max(time.perf_counter() - t0, 1e-6) * 1.2
-    budget = 150.0 / (args.steps + args.warmup)
-    n = int(min(max(rate * budget, 64), BATCH))
-    n_batches = IMG_W * IMG_H // BATCH
-    def step(i):
-        lo = (i * 37 % n_batches) * BATCH
-        oracle_batch(lt, field, ids[lo:lo + n])
-    for i in range(args.warmup):
-        step(i)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(args.warmup + i)
-    dt = time.perf_counter() - t0
-    value = n * args.steps / dt
+    wl = Workload(args.workload, args.grid)
+    torch.set_num_threads(os.cpu_count() or 1)
+    kind, cores = "reference", torch.get_num_threads()
+    try:
+        value, dt = time_reference(wl, "cpu", args.warmup, args.steps)
+        sample = (f"4096 rays per step, unmodified PyTorch reference (baseline/_ref), LocalTensorfs.forward, "
+                  f"torch {torch.__version__}, {cores} threads")
+    except Exception as e:
+        print(f"bench: reference unavailable ({e}); timing the oracle port", file=sys.stderr)
+        if wl.name not in ("cfg2", "distB"):
+            emit({"impl": "reference", "unavailable": f"reference not importable and the oracle port covers cfg2 only ({e})"})
+            return
+        kind, cores = "port", os.cpu_count()
+        lt = wl.build(__import__("localrf_b200").LocalTensorfs, quiet=True)
+        field = oracle_field(lt)
+        ids = frame_ids().numpy()
+        n_batches = IMG_W * IMG_H // BATCH
+        def step(i):
+            lo = (i * 37 % n_batches) * BATCH
+            oracle_batch(lt, field, ids[lo:lo + BATCH])
+        for i in range(args.warmup):
+            step(i)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        dt = time.perf_counter() - t0
+        value = BATCH * args.steps / dt
+        sample = f"4096 rays per step, oracle/lrf_oracle.c, OpenMP {cores} threads"
     emit({
         "impl": "reference", "metric": "rays/sec at 300^3 VM grid, 4096-ray batch", "value": value,
         "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg2: TensorVMSplit {GRID}^3 (seed 0, random init), 800x800 frame, "
-                               f"4096-ray batches; each step = the first {n} rays of a batch"},
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{n} rays per step, oracle/lrf_oracle.c, OpenMP {os.cpu_count()} threads"},
+        "config": {"workload": wl.describe(), "rays_per_batch": BATCH},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
 
+# ---- our arm ---------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=157)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "distB", "incoherent", "cfg3", "cfg5"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong", "frame"])
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--grid", type=int, default=GRID)
+    ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--grid", type=int, default=None)
     args = ap.parse_args()
     quiet_stdout()
+    if args.steps is None:
+        args.steps = 20 if args.impl == "reference" else 157
     if args.impl == "reference":
         return run_reference(args)
     if args.warmup < 3:
         args.warmup = 3
 
-    import ctypes as C
     import localrf_b200 as L
-    from localrf_b200 import _lib
-    from localrf_b200.tensorf import _ptr, _stream
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU port")
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU reference")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -274,45 +483,65 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    lt = build_scene(dev, args.grid)
-    rf = lt.tensorfs[0]
-    ids_dev = frame_ids().to(dev)
-    n_batches = IMG_W * IMG_H // BATCH     # 156 full batches (+ a ragged one the bench skips)
-
-    # ---- device-resident step: direct C-ABI launch --------------------------------------------------
-    view = torch.tensor([0], device=dev)
-    z = rf.sample_table(False, -1, dev)
-    fs, prep = rf.field_and_prepared(z)
-    S = z.numel()
-    c2w = lt.get_cam2world(view).detach().contiguous()
-    intr = torch.cat([lt.focal(IMG_W).detach().reshape(1), lt.center(IMG_W, IMG_H).detach().reshape(2)]).contiguous()
-    expo = torch.stack(list(lt.exposure))[view].detach().contiguous()
-    blend = torch.ones(1, 1, device=dev)
-    rgb = torch.empty(BATCH, 3, device=dev); depth = torch.empty(BATCH, device=dev)
-    gathered = torch.empty(world * BATCH, 4, device=dev) if world > 1 else None
-    pix = torch.empty(BATCH, 4, device=dev) if world > 1 else None
+    wl = Workload(args.workload, args.grid)
+    lt = wl.build(L.LocalTensorfs, quiet=True).to(dev)
+    kw = wl.call_kwargs(lt, dev)
+    ids_host, views_host = wl.batches()
+    n_batches = ids_host.shape[0]
+    scaling = args.scaling if world > 1 else "weak"
+    if scaling == "frame":                                   # step = the whole frame, split N ways
+        ids_host = frame_ids()[None]
+        views_host = [torch.tensor([0])]
+        n_batches = 1
+    rays_per_step_global = {"weak": world * BATCH, "strong": BATCH, "frame": IMG_W * IMG_H}[scaling]
+    ids_dev = ids_host.to(dev)
+    views_dev = {id(v): v.to(dev) for v in views_host}      # one device tensor per distinct view list
     stats = torch.zeros(2, dtype=torch.int64, device=dev)
-    b = _lib.LrfBatch(); o = _lib.LrfOutputs()
-    b.n_rays = BATCH; b.W, b.H = IMG_W, IMG_H; b.fov360 = 0
-    b.intrinsics = intr.data_ptr(); b.cam2world = c2w.data_ptr(); b.n_views = 1
-    b.blend = blend.data_ptr(); b.blend_stride = 1; b.exposure = expo.data_ptr()
-    b.accumulate = 0; b.finalize = 1; b.white_bg = 1; b.floater_thresh = 0.0
-    o.rgb, o.depth, o.stats = rgb.data_ptr(), depth.data_ptr(), stats.data_ptr()
-    if world > 1:
-        o.pix = pix.data_ptr()          # interleaved (r,g,b,depth): one all-gather, no repack kernels
-    lib = _lib.lib()
-    stream = _stream(dev)
 
-    def step(i):
-        bi = ((i * world + rank) * 37) % n_batches        # a different batch of the frame each step
-        b.ray_ids = ids_dev.data_ptr() + 8 * BATCH * bi
-        _lib.check(lib.lrf_render(C.byref(fs), _ptr(prep), C.byref(b), C.byref(o), stream))
+    # ---- multi-GPU plumbing ----------------------------------------------------------------------------
+    from localrf_b200.dist import PixelExchange, shard_bounds
+    xch, exchange_kind = None, None
+    if world > 1:
+        exchange_kind = args.exchange
+        if args.exchange == "fused":
+            try:
+                xch = PixelExchange(rays_per_step_global, device=dev)
+                exchange_kind = "fused (multimem stores)" if xch.mc_ptr else "fused (peer stores)"
+            except Exception as e:
+                print(f"bench: symmetric memory unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+                exchange_kind = "nccl (fused unavailable)"
+        if xch is None:
+            shard = {"weak": BATCH, "strong": -(-BATCH // world // 8) * 8, "frame": -(-IMG_W * IMG_H // world // 8) * 8}[scaling]
+            gathered = torch.empty(world * shard, 4, device=dev)
+            pix_pad = torch.zeros(shard, 4, device=dev)
+
+    def shard_of(n):
+        """(lo, hi, row offset in the gathered buffer) of this rank's rays for one step"""
+        if scaling == "weak":
+            return 0, n, rank * n
+        lo, hi = shard_bounds(n, rank, world)
+        return lo, hi, lo
+
+    def batch_index(i):
+        return ((i * world + rank) * 37) % n_batches if scaling == "weak" else (i * 37) % n_batches
+
+    def step(i, ids_all, out=None, want_stats=True):
+        bi = batch_index(i)
+        ids = ids_all[bi]
+        lo, hi, row = shard_of(ids.shape[0])
+        view = views_dev[id(views_host[bi])]
+        if xch is not None:
+            return lt(ids[lo:hi], view, IMG_W, IMG_H, stats=stats if want_stats else None,
+                      exchange=(xch, row), **kw)
+        r = lt(ids[lo:hi], view, IMG_W, IMG_H, stats=stats if want_stats else None, out=out, **kw)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, pix)
+            pix_pad[:hi - lo, :3] = r[0]; pix_pad[:hi - lo, 3] = r[1]
+            dist.all_gather_into_tensor(gathered, pix_pad)
+        return r
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for i in range(args.warmup):
-        step(i); flush.zero_()
+        step(i, ids_dev); flush.zero_()
     torch.cuda.synchronize()
     stats.zero_()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -322,9 +551,9 @@ def main():
     torch.cuda.synchronize()
     sampler.start()
     for i in range(args.steps):
-        flush.zero_()                       # L2 flush between timed iterations (outside the events)
+        flush.zero_(); flush.zero_()         # L2 flush between timed iterations (outside the events)
         ev[i][0].record()
-        step(args.warmup + i)
+        step(args.warmup + i, ids_dev)
         ev[i][1].record()
     torch.cuda.synchronize()
     if world > 1:
@@ -336,64 +565,70 @@ def main():
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms)
     st = stats.cpu().tolist()
-    value = world * BATCH * args.steps / (total_ms * 1e-3)
+    value = rays_per_step_global * args.steps / (total_ms * 1e-3)
+    launches = [len(p.launches) for p in lt.__dict__.get("_plans", {}).values()]
+    gpu_launches = args.steps * (max(launches) if launches else 1) + (args.steps if xch is not None else 0)
 
-    # roofline of the fused kernel (rank 0's launches)
-    bytes_total = st[0] * 576 + st[1] * 1728 + BATCH * args.steps * 40
-    kern_ms = sum(times_ms) if world == 1 else None
+    # roofline of the fused kernel (this rank's launches; N=1 only: with N>1 the events also cover the exchange)
     peak, peak_src = peaks()
     roofline = None
     if world == 1:
-        achieved = bytes_total / (kern_ms * 1e-3) / 1e9
+        rays_total = BATCH * args.steps
+        bytes_total = st[0] * 576 + st[1] * 1728 + rays_total * 40
+        achieved = bytes_total / (sum(times_ms) * 1e-3) / 1e9
+        traffic, traffic_src = traffic_for(wl.name)
+        n_kern = max(launches) if launches else 1
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the
-                    # committed `ncu --set full` capture (profiles/r1_v3_streaming.md): 4.08 MB + 0 B
-                    "traffic": 4.08e6, "traffic_unit": "bytes per launch (ncu, profiles/r1_v3_streaming.md)",
-                    "algorithmic_bytes_per_launch": bytes_total / args.steps,
-                    "peak_source": peak_src,
-                    "kernel": "lrf::render_kernel",
-                    "bytes_per_ray": bytes_total / (BATCH * args.steps),
-                    "density_samples_per_ray": st[0] / (BATCH * args.steps),
-                    "app_samples_per_ray": st[1] / (BATCH * args.steps),
-                    "note": "algorithmic gather bytes (every texel fetch counted); the 33 MB field is "
-                            "L2-resident, so DRAM counters read far lower (profiles/)"}
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": bytes_total / (args.steps * n_kern),
+                    "launches_per_step": n_kern, "peak_source": peak_src, "kernel": "lrf::render_kernel",
+                    "bytes_per_ray": bytes_total / rays_total,
+                    "density_samples_per_ray": st[0] / rays_total,
+                    "app_samples_per_ray": st[1] / rays_total,
+                    "note": "algorithmic gather bytes (every texel fetch counted, all active fields); a 300^3 "
+                            "field (33 MB) is L2-resident, so DRAM counters read far lower (profiles/)"}
 
-    # ---- e2e: public API, host buffers, every step ---------------------------------------------------
-    ids_host = frame_ids().pin_memory()
-    rgb_host = torch.empty(BATCH, 3, pin_memory=True)
-    depth_host = torch.empty(BATCH, pin_memory=True)
-    e2e_steps = args.steps
+    # ---- e2e: public API from pinned host ids to pinned host pixels, every step ----------------------------
+    ids_pin = ids_host.pin_memory()
+    n_loc = max(shard_of(ids_host.shape[1])[1] - shard_of(ids_host.shape[1])[0], 1)
+    rgb_host = torch.empty(n_loc, 3).pin_memory()
+    depth_host = torch.empty(n_loc).pin_memory()
+    full_host = torch.empty(rays_per_step_global, 4).pin_memory() if world > 1 else None
+    stream = torch.cuda.current_stream(dev)
+
     def e2e_step(i):
-        bi = ((i * world + rank) * 37) % n_batches
-        ids = ids_host[bi * BATCH:(bi + 1) * BATCH].to(dev, non_blocking=True)
-        with torch.no_grad():
-            r, d, _, _ = lt(ids, view, IMG_W, IMG_H, is_train=False, chunk=BATCH)
-        rgb_host.copy_(r, non_blocking=True)
-        depth_host.copy_(d, non_blocking=True)
-        torch.cuda.synchronize()
+        if world == 1:
+            step(i, ids_pin, out=(rgb_host, depth_host), want_stats=False)
+        else:
+            step(i, ids_pin, want_stats=False)
+            src = xch.gathered(rays_per_step_global) if xch is not None else gathered[:rays_per_step_global]
+            full_host[:src.shape[0]].copy_(src, non_blocking=True)
+        stream.synchronize()
+
     for i in range(args.warmup):
         e2e_step(i)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
+    for i in range(args.steps):
         e2e_step(args.warmup + i)
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * BATCH * e2e_steps / float(e2e_s)
+    e2e_value = rays_per_step_global * args.steps / float(e2e_s)
+    h2d = n_loc * 8
+    d2h = n_loc * 16 if world == 1 else rays_per_step_global * 16
 
-    # ---- whole frame through the API (one fused launch for all 640k rays), informational ------------
+    # ---- whole frame through the API (one fused launch per field for all 640k rays), informational -----------
     frame = None
-    if world == 1:
-        all_ids = ids_host
+    if world == 1 and wl.name in ("cfg2", "distB", "cfg3"):
+        all_ids = frame_ids().pin_memory()
+        view0 = views_dev[id(views_host[0])]
         def frame_call():
-            ids = all_ids.to(dev, non_blocking=True)
             with torch.no_grad():
-                r, d, _, _ = lt(ids, view, IMG_W, IMG_H, is_train=False, chunk=BATCH)
+                r, d, _, _ = lt(all_ids.to(dev, non_blocking=True), view0, IMG_W, IMG_H, **kw)
             r.cpu(); d.cpu()
         frame_call()
         torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -405,28 +640,45 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        cpu = cpu_baseline(build_scene("cpu", args.grid))
+    cpu, ref_gpu = None, None
+    if world == 1:
+        if not args.no_reference_gpu:
+            try:
+                del flush
+                torch.cuda.empty_cache()
+                v, dt = time_reference(wl, dev, 2, 5)
+                ref_gpu = {"value": v, "unit": "rays/s", "what": "the unmodified PyTorch reference (baseline/_ref), "
+                           f"device=cuda on this GPU, same workload, 5 batches of 4096 rays after 2 warm-ups, {dt:.3f} s"}
+            except Exception as e:
+                ref_gpu = {"unavailable": str(e)[:200]}
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline(wl)
     line = {
         "metric": "rays/sec at 300^3 VM grid, 4096-ray batch", "value": value, "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak" if scaling == "weak" else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "dtype_note": "fp32 storage and arithmetic; the two dense MLP layers run on tcgen05 as three bf16 "
                       "products of hi/lo-split fp32 operands with fp32 TMEM accumulators (1e-7 of fp32 on rgb, "
                       "tests/test_gpu_parity.py::test_tensor_core_mlp_vs_torch_fp32)",
-        "config": {"workload": f"cfg2: TensorVMSplit {args.grid}^3 (reference ctor, seed 0, random init), "
-                               "800x800 pinhole frame fov 85.6 identity pose, 4096-ray batches; "
-                               "step = one batch, steps walk the frame's batches",
-                   "rays_per_batch": BATCH, "samples_per_ray": S, "l2": "256 MiB write between timed steps",
-                   "parallelism": f"ray-batch data parallel x{world}" + (", all-gather [4096,4] per step" if world > 1 else "")},
+        "config": {"workload": wl.describe(), "workload_key": wl.name, "rays_per_batch": BATCH,
+                   "rays_per_step_global": rays_per_step_global,
+                   "l2": "2 x 256 MiB writes between timed steps",
+                   "sharding": {"weak": "every rank its own 4096-ray batch per step",
+                                "strong": "each 4096-ray batch split over the ranks (BASELINE config 4)",
+                                "frame": "the frame's 640000 rays split over the ranks, one exchange per frame"}[scaling],
+                   "exchange": exchange_kind,
+                   "parallelism": f"ray-batch data parallel x{world}"},
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": BATCH * 8,
-                "d2h_bytes_per_step": BATCH * 16},
-        "gpu_launches": args.steps,
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "how": "pinned host ray ids read and pinned host rgb/depth written by the kernel over PCIe "
+                       "(zero-copy), stream sync per step" if world == 1 else
+                       "pinned host ids (zero-copy), fused exchange, D2H copy of the gathered pixels, sync per step"},
+        "gpu_launches": gpu_launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "reference_gpu": ref_gpu,
         "frame_api": frame,
     }
     emit(line)

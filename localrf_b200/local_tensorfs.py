@@ -461,7 +461,7 @@ class LocalTensorfs(torch.nn.Module):
                 plan, res = res
                 # the key holds ids of caller objects: keep them alive so the ids cannot be recycled
                 plan.key_refs = (view_ids, cam2world, world2rf, blending_weights)
-                if len(plans) >= 64:
+                if len(plans) >= 256:
                     plans.clear()
                 plans[key] = plan
             return res
