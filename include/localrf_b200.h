@@ -208,6 +208,39 @@ int lrf_render_backward(const LrfField *field, const void *prepared_bwd, const f
 int lrf_peer_barrier(unsigned long long *const *peer_flags, int32_t rank, int32_t world,
                      unsigned long long seq, lrf_stream_t stream);
 
+/* ---- schedule-time operators on the field's tensors ---------------------------
+ * Occupancy-mask rebuild.  replaces: getDenseAlpha + updateAlphaMask (models/tensorBase.py:501-536), which
+ * move the model to the CPU and loop over slabs.  dims = (gx,gy,gz) of the lattice (the caller passes
+ * gridSize/2, local_tensorfs.py:264-266); `length` = stepSize.  alpha_scratch [gx][gy][gz] receives
+ * getDenseAlpha()'s alpha (an existing mask in `field` culls as compute_alpha does, :538-558); mask
+ * [gz][gy][gx] receives {0,1} = max_pool3d(3, pad 1)(clamp(alpha,0,1)) >= thres; *kept += #ones.
+ * mask may be NULL (dense alpha only). */
+int lrf_alpha_mask_build(const LrfField *field, const int32_t dims[3], float length, float thres,
+                         float *alpha_scratch, float *mask, unsigned long long *kept,
+                         lrf_stream_t stream);
+/* Grid upsampling.  replaces: F.interpolate(bilinear, align_corners=True) of up_sampling_VM
+ * (models/tensoRF.py:198-221) on one channel-last tensor: src [H][W][C] -> dst [H2][W2][C] (lines: W = W2 = 1).
+ * C must be a multiple of 4. */
+int lrf_upsample(const float *src, int32_t H, int32_t W, float *dst, int32_t H2, int32_t W2, int32_t C,
+                 lrf_stream_t stream);
+/* density_L1 (models/tensoRF.py:83-92) without the 8*G^3 intermediate: *sum += sum_n sqrt(clamp(
+ * feature2density(f[n]), 1e-5)) over the G^3 flat indices (the caller divides by G^3).  The backward
+ * ACCUMULATES d(mean)/d(plane_i, line_i) * (*grad_out) into buffers laid out like the parameters. */
+int lrf_density_l1(const LrfField *field, double *sum, lrf_stream_t stream);
+int lrf_density_l1_backward(const LrfField *field, const float *grad_out, float *const d_plane[3],
+                            float *const d_line[3], lrf_stream_t stream);
+/* TVLoss (utils/utils.py:293-312) pieces on one channel-last [H][W][C] tensor: sums[0] += sum of squared
+ * differences along H, sums[1] += along W.  Backward: dx += (*grad_out) * (kh * d sums[0]/dx + kw * d sums[1]/dx). */
+int lrf_tv_sums(const float *x, int32_t H, int32_t W, int32_t C, double *sums, lrf_stream_t stream);
+int lrf_tv_sums_backward(const float *x, int32_t H, int32_t W, int32_t C, const float *grad_out, float kh,
+                         float kw, float *dx, lrf_stream_t stream);
+/* sample_ray (models/tensorBase.py:396-417): ray-AABB entry distance clamped to [near, far], S uniform steps
+ * of `step` from there (+ jitter[r] steps when jitter != NULL: the train-mode draw, one per ray), points and
+ * the inside-the-box mask.  rays [N][6]; aabb = {min xyz, max xyz}; pts [N][S][3], z [N][S], inside [N][S]. */
+int lrf_sample_ray(const float *rays, const float *jitter, int64_t N, int32_t S, const float aabb[6],
+                   float near, float far, float step, float *pts, float *z, unsigned char *inside,
+                   lrf_stream_t stream);
+
 /* [C][H][W] (contiguous NCHW parameter of the reference) -> [H][W][C] */
 int lrf_repack_nchw_to_nhwc(const float *src, float *dst, int32_t C, int32_t H, int32_t W,
                             lrf_stream_t stream);

@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_CSRC, "liblrf_b200.so")
-SOURCES = ["lrf_render.cu", "lrf_aux.cu", "lrf_grad.cu", "lrf_backward.cu", "lrf_abi.cu"]
+SOURCES = ["lrf_render.cu", "lrf_aux.cu", "lrf_grad.cu", "lrf_backward.cu", "lrf_sched.cu", "lrf_abi.cu"]
 HEADERS = ["lrf_common.cuh", "lrf_device.cuh", os.path.join("..", "..", "include", "localrf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -75,7 +75,9 @@ EXPORTS = ["lrf_version", "lrf_sizeof", "lrf_last_error", "lrf_prepared_bytes", 
            "lrf_render", "lrf_mlp_forward", "lrf_app_products", "lrf_density_feature_backward",
            "lrf_app_products_backward", "lrf_density_feature", "lrf_app_feature", "lrf_repack_nchw_to_nhwc",
            "lrf_launch_info", "lrf_prepared_backward_bytes", "lrf_backward_scratch_bytes",
-           "lrf_field_prepare_backward", "lrf_render_backward", "lrf_peer_barrier"]
+           "lrf_field_prepare_backward", "lrf_render_backward", "lrf_peer_barrier",
+           "lrf_alpha_mask_build", "lrf_upsample", "lrf_density_l1", "lrf_density_l1_backward", "lrf_tv_sums",
+           "lrf_tv_sums_backward", "lrf_sample_ray"]
 
 
 def _stale():
@@ -150,6 +152,14 @@ def lib():
     L.lrf_field_prepare_backward.argtypes = [C.POINTER(LrfField), _vp, _vp]
     L.lrf_render_backward.argtypes = [C.POINTER(LrfField), _vp, _vp, C.c_int64, C.c_int32, _vp, _vp,
                                       C.POINTER(LrfGradients), _vp, C.c_size_t, _vp]
+    L.lrf_alpha_mask_build.argtypes = [C.POINTER(LrfField), C.c_int32 * 3, C.c_float, C.c_float, _vp, _vp, _vp, _vp]
+    L.lrf_upsample.argtypes = [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]
+    L.lrf_density_l1.argtypes = [C.POINTER(LrfField), _vp, _vp]
+    L.lrf_density_l1_backward.argtypes = [C.POINTER(LrfField), _vp, _vp * 3, _vp * 3, _vp]
+    L.lrf_tv_sums.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]
+    L.lrf_tv_sums_backward.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_float, C.c_float, _vp, _vp]
+    L.lrf_sample_ray.argtypes = [_vp, _vp, C.c_int64, C.c_int32, C.c_float * 6, C.c_float, C.c_float, C.c_float,
+                                 _vp, _vp, _vp, _vp]
     L.lrf_peer_barrier.argtypes = [C.POINTER(_vp), C.c_int32, C.c_int32, C.c_uint64, _vp]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError if the header and the library ever drift apart

@@ -22,6 +22,20 @@ cudaError_t launch_density_feature(const FieldDev& F, const float* xyz, long lon
 cudaError_t launch_app_feature(const FieldDev& F, const float* basis, const float* xyz,
                                long long M, float* out, cudaStream_t stream);
 cudaError_t launch_repack(const float* src, float* dst, int C, long long HW, cudaStream_t stream);
+cudaError_t launch_alpha_mask_build(const FieldDev& F, const float* aabb_max, const int* dims, float length,
+                                    float thres, float* alpha_scratch, float* mask,
+                                    unsigned long long* kept, int n_sms, cudaStream_t stream);
+cudaError_t launch_upsample(const float* src, int H, int W, float* dst, int H2, int W2, int C, int n_sms,
+                            cudaStream_t stream);
+cudaError_t launch_density_l1(const FieldDev& F, double* sum, int n_sms, cudaStream_t stream);
+cudaError_t launch_density_l1_backward(const FieldDev& F, const float* gout, float* const* d_plane,
+                                       float* const* d_line, cudaStream_t stream);
+cudaError_t launch_tv(const float* x, int H, int W, int C, double* sums, int n_sms, cudaStream_t stream);
+cudaError_t launch_tv_backward(const float* x, int H, int W, int C, const float* gout, float kh, float kw,
+                               float* dx, int n_sms, cudaStream_t stream);
+cudaError_t launch_sample_ray(const float* rays, const float* jitter, long long N, int S, const float* aabb,
+                              float near, float far, float step, float* pts, float* z,
+                              unsigned char* inside, int n_sms, cudaStream_t stream);
 cudaError_t launch_peer_barrier(unsigned long long* const* peer_flags, int rank, int world,
                                 unsigned long long seq, cudaStream_t stream);
 cudaError_t launch_app_products(const FieldDev& F, const float* xyz, long long M, float* out,
@@ -388,6 +402,97 @@ int lrf_render_backward(const LrfField* f, const void* prepared_bwd, const float
                                                   static_cast<const float*>(prepared_bwd), *g, scratch,
                                                   d.n_sms, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "render_backward");
+  return LRF_OK;
+}
+
+int lrf_alpha_mask_build(const LrfField* f, const int32_t dims[3], float length, float thres,
+                         float* alpha_scratch, float* mask, unsigned long long* kept, lrf_stream_t stream) {
+  lrf::FieldDev F;
+  int rc = make_field(f, false, false, nullptr, F);
+  if (rc != LRF_OK) return rc;
+  if (!dims || dims[0] < 1 || dims[1] < 1 || dims[2] < 1) return fail(LRF_ERR_INVALID, "lattice dims must be >= 1");
+  if (!alpha_scratch) return fail(LRF_ERR_INVALID, "alpha_scratch is NULL");
+  if (mask && !kept) return fail(LRF_ERR_INVALID, "kept is NULL");
+  DevInfo d;
+  if ((rc = device_info(d)) != LRF_OK) return rc;
+  const int dd[3] = {dims[0], dims[1], dims[2]};
+  cudaError_t e = lrf::launch_alpha_mask_build(F, f->aabb + 3, dd, length, thres, alpha_scratch, mask, kept,
+                                               d.n_sms, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "alpha_mask_build");
+  return LRF_OK;
+}
+
+int lrf_upsample(const float* src, int32_t H, int32_t W, float* dst, int32_t H2, int32_t W2, int32_t C,
+                 lrf_stream_t stream) {
+  if (!src || !dst || H < 1 || W < 1 || H2 < 1 || W2 < 1 || C < 4 || (C & 3))
+    return fail(LRF_ERR_INVALID, "bad upsample arguments (C must be a positive multiple of 4)");
+  if (((uintptr_t)src | (uintptr_t)dst) & 15) return fail(LRF_ERR_INVALID, "upsample buffers must be 16-byte aligned");
+  DevInfo d;
+  int rc = device_info(d);
+  if (rc != LRF_OK) return rc;
+  cudaError_t e = lrf::launch_upsample(src, H, W, dst, H2, W2, C, d.n_sms, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "upsample_kernel");
+  return LRF_OK;
+}
+
+int lrf_density_l1(const LrfField* f, double* sum, lrf_stream_t stream) {
+  lrf::FieldDev F;
+  int rc = make_field(f, false, false, nullptr, F);
+  if (rc != LRF_OK) return rc;
+  if (!sum) return fail(LRF_ERR_INVALID, "sum is NULL");
+  DevInfo d;
+  if ((rc = device_info(d)) != LRF_OK) return rc;
+  cudaError_t e = lrf::launch_density_l1(F, sum, d.n_sms, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "density_l1_fwd_kernel");
+  return LRF_OK;
+}
+
+int lrf_density_l1_backward(const LrfField* f, const float* grad_out, float* const d_plane[3],
+                            float* const d_line[3], lrf_stream_t stream) {
+  lrf::FieldDev F;
+  int rc = make_field(f, false, false, nullptr, F);
+  if (rc != LRF_OK) return rc;
+  if (!grad_out) return fail(LRF_ERR_INVALID, "grad_out is NULL");
+  if (!d_plane || !d_line) return fail(LRF_ERR_INVALID, "gradient pointer arrays are NULL");
+  for (int i = 0; i < 3; ++i)
+    if (!d_plane[i] || !d_line[i]) return fail(LRF_ERR_INVALID, "gradient buffer is NULL");
+  cudaError_t e = lrf::launch_density_l1_backward(F, grad_out, d_plane, d_line, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "density_l1_bwd_kernel");
+  return LRF_OK;
+}
+
+int lrf_tv_sums(const float* x, int32_t H, int32_t W, int32_t C, double* sums, lrf_stream_t stream) {
+  if (!x || !sums || H < 1 || W < 1 || C < 1) return fail(LRF_ERR_INVALID, "bad tv arguments");
+  DevInfo d;
+  int rc = device_info(d);
+  if (rc != LRF_OK) return rc;
+  cudaError_t e = lrf::launch_tv(x, H, W, C, sums, d.n_sms, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "tv_fwd_kernel");
+  return LRF_OK;
+}
+
+int lrf_tv_sums_backward(const float* x, int32_t H, int32_t W, int32_t C, const float* grad_out, float kh,
+                         float kw, float* dx, lrf_stream_t stream) {
+  if (!x || !dx || !grad_out || H < 1 || W < 1 || C < 1) return fail(LRF_ERR_INVALID, "bad tv arguments");
+  DevInfo d;
+  int rc = device_info(d);
+  if (rc != LRF_OK) return rc;
+  cudaError_t e = lrf::launch_tv_backward(x, H, W, C, grad_out, kh, kw, dx, d.n_sms, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "tv_bwd_kernel");
+  return LRF_OK;
+}
+
+int lrf_sample_ray(const float* rays, const float* jitter, int64_t N, int32_t S, const float aabb[6],
+                   float near, float far, float step, float* pts, float* z, unsigned char* inside,
+                   lrf_stream_t stream) {
+  if (N < 0 || S < 1 || !aabb) return fail(LRF_ERR_INVALID, "bad sample_ray sizes");
+  if (N > 0 && (!rays || !pts || !z || !inside)) return fail(LRF_ERR_INVALID, "sample_ray buffer is NULL");
+  DevInfo d;
+  int rc = device_info(d);
+  if (rc != LRF_OK) return rc;
+  cudaError_t e = lrf::launch_sample_ray(rays, jitter, N, S, aabb, near, far, step, pts, z, inside, d.n_sms,
+                                         (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "sample_ray_kernel");
   return LRF_OK;
 }
 

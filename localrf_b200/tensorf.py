@@ -157,6 +157,90 @@ class _RenderFn(torch.autograd.Function):
                 d_w3, d_b3)
 
 
+class _DensityL1Fn(torch.autograd.Function):
+    """density_L1 (tensoRF.py:83-92) as two streaming kernels: nothing of size G^3 is materialised
+    (the reference's bmm intermediate is 8*G^3 floats: 8.4 GB at 640^3)."""
+
+    @staticmethod
+    def forward(ctx, module, *grids):
+        dev = grids[0].device
+        acc = torch.zeros(1, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            fs, _ = module._field_struct(None, need_mlp=False)
+            _lib.check(_lib.lib().lrf_density_l1(C.byref(fs), _ptr(acc), _stream(dev)))
+        ctx.module = module
+        n = 1
+        for g in module._grid_host:
+            n *= g
+        return (acc / n).to(torch.float32)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        m = ctx.module
+        dev = m.density_plane[0].device
+        cl = torch.channels_last
+        d_planes = [torch.zeros_like(p, memory_format=cl) for p in m.density_plane]
+        d_lines = [torch.zeros_like(p, memory_format=cl) for p in m.density_line]
+        gg = g.detach().to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(dev):
+            fs, _ = m._field_struct(None, need_mlp=False)
+            pp = (C.c_void_p * 3)(*[t.data_ptr() for t in d_planes])
+            lp = (C.c_void_p * 3)(*[t.data_ptr() for t in d_lines])
+            _lib.check(_lib.lib().lrf_density_l1_backward(C.byref(fs), _ptr(gg), pp, lp, _stream(dev)))
+        return (None, *d_planes, *d_lines)
+
+
+class _TVFn(torch.autograd.Function):
+    """sum_i coef_plane * TVLoss(plane_i) + coef_line * TVLoss(line_i) (tensoRF.py:94-110 with
+    utils/utils.py:293-312) on the channel-last tensors: one reduction kernel per tensor forward, one
+    stencil kernel per tensor backward -- no transposed / shifted copies."""
+
+    @staticmethod
+    def _geom(t):
+        c, h, w = t.shape[1], t.shape[2], t.shape[3]
+        kh = 1.0 / (c * (h - 1) * w) if h > 1 else 0.0          # 1 / numel of the H-difference tensor
+        kw = 1.0 / (c * h * (w - 1)) if w > 1 else 0.0
+        return c, h, w, kh, kw
+
+    @staticmethod
+    def forward(ctx, weight, coefs, *tensors):
+        dev = tensors[0].device
+        sums = torch.zeros(len(tensors), 2, dtype=torch.float64, device=dev)
+        lib = _lib.lib()
+        scale = []
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            for i, t in enumerate(tensors):
+                c, h, w, kh, kw = _TVFn._geom(t)
+                _lib.check(lib.lrf_tv_sums(_ptr(t.detach()), h, w, c, C.c_void_p(sums.data_ptr() + 16 * i), st))
+                scale.append([2.0 * weight * coefs[i] * kh, 2.0 * weight * coefs[i] * kw])
+        ctx.scale = scale
+        ctx.save_for_backward(*tensors)
+        return (sums * torch.tensor(scale, dtype=torch.float64, device=dev)).sum().to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        tensors = ctx.saved_tensors
+        dev = tensors[0].device
+        gg = g.detach().to(torch.float32).reshape(1).contiguous()
+        grads = []
+        lib = _lib.lib()
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            for (kh, kw), t in zip(ctx.scale, tensors):
+                d = torch.zeros_like(t, memory_format=torch.channels_last)
+                c, h, w = t.shape[1], t.shape[2], t.shape[3]
+                _lib.check(lib.lrf_tv_sums_backward(_ptr(t.detach()), h, w, c, _ptr(gg), kh, kw, _ptr(d), st))
+                grads.append(d)
+        return (None, None, *grads)
+
+
+def _cl_empty(c, h, w, device):
+    """uninitialised [1,c,h,w] float32 tensor whose memory is [h][w][c] (channels_last strides, also for
+    the degenerate w == 1 of the line tensors)."""
+    return torch.empty(1, h, w, c, dtype=torch.float32, device=device).permute(0, 3, 1, 2)
+
+
 class AlphaGridMask(torch.nn.Module):
     """models/tensorBase.py:38-62 -- binary occupancy volume, trilinearly sampled."""
 
@@ -624,30 +708,58 @@ class TensorBase(torch.nn.Module):
             sigma[keep] = self.feature2density(feat)
         return 1 - torch.exp(-sigma * length).view(xyz_locs.shape[:-1])
 
+    def _alpha_lattice(self, gridSize, want_mask):
+        """One lrf_alpha_mask_build call: dense alpha [gx,gy,gz] (+ the pooled / thresholded mask
+        [gz,gy,gx] and the number of kept voxels)."""
+        dims = [int(g) for g in gridSize]
+        dev = self.aabb.device
+        _require_cuda(self.aabb, "aabb")
+        alpha = torch.empty(dims, dtype=torch.float32, device=dev)
+        mask = torch.empty(dims[::-1], dtype=torch.float32, device=dev) if want_mask else None
+        kept = torch.zeros(1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            fs, _ = self._field_struct(None, need_mlp=False)
+            _lib.check(_lib.lib().lrf_alpha_mask_build(
+                C.byref(fs), (C.c_int32 * 3)(*dims), float(self.stepSize), float(self.alphaMask_thres),
+                _ptr(alpha), _ptr(mask), _ptr(kept), _stream(dev)))
+        return alpha, mask, kept
+
     @torch.no_grad()
     def getDenseAlpha(self, gridSize=None):
-        """tensorBase.py:501-515 -- alpha on a dense lattice of the aabb, slab by slab."""
-        gridSize = self.gridSize if gridSize is None else gridSize
-        dev = self.aabb.device
-        axes = [torch.linspace(0, 1, int(n), device=dev) for n in gridSize]
-        lattice = torch.stack(torch.meshgrid(*axes, indexing="ij"), -1)
-        lattice = self.aabb[0] * (1 - lattice) + self.aabb[1] * lattice
-        alpha = torch.zeros_like(lattice[..., 0])
-        for i in range(int(gridSize[0])):
-            alpha[i] = self.compute_alpha(lattice[i].view(-1, 3), self.stepSize).view(
-                int(gridSize[1]), int(gridSize[2]))
-        return alpha
+        """tensorBase.py:501-515 -- alpha on a dense lattice of the aabb: one kernel launch."""
+        gridSize = self._grid_host if gridSize is None else gridSize
+        return self._alpha_lattice(gridSize, False)[0]
 
     @torch.no_grad()
     def updateAlphaMask(self, gridSize=(200, 200, 200)):
-        """tensorBase.py:517-536 -- rebuilt ON THE DEVICE (the reference moves the model to the CPU)."""
+        """tensorBase.py:517-536 -- rebuilt ON THE DEVICE by two kernels (lattice density + 3x3x3
+        max-pool / threshold); the reference moves the model to the CPU and loops over slabs."""
         gridSize = tuple(int(g) for g in gridSize)
-        alpha = self.getDenseAlpha(gridSize).clamp(0, 1).transpose(0, 2).contiguous()[None, None]
-        alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1).view(gridSize[::-1])
-        alpha = (alpha >= self.alphaMask_thres).to(alpha.dtype)
-        self.alphaMask = AlphaGridMask(self.aabb.device, self.aabb.detach(), alpha)
-        kept = float(alpha.sum()) / (gridSize[0] * gridSize[1] * gridSize[2]) * 100
-        print(f"alpha rest %%%f" % kept)
+        _, mask, kept = self._alpha_lattice(gridSize, True)
+        self.alphaMask = AlphaGridMask(self.aabb.device, self.aabb.detach(), mask)
+        total = gridSize[0] * gridSize[1] * gridSize[2]
+        print(f"alpha rest %%%f" % (float(kept) / total * 100))
+
+    # -- sample_ray (tensorBase.py:396-417): the ray-AABB sampler (not on LocalTensorfs' render path,
+    #    which samples contracted space; kept as the utility north_star names) -----------------------
+    def sample_ray(self, rays_o, rays_d, is_train=True, N_samples=-1):
+        """-> (rays_pts [N,S,3], interpx [N,S], inside-the-aabb mask [N,S]) like the reference."""
+        _require_cuda(rays_o, "rays_o")
+        dev = rays_o.device
+        S = int(N_samples if N_samples > 0 else self.nSamples)
+        rays = torch.cat([rays_o.detach().reshape(-1, 3), rays_d.detach().reshape(-1, 3)], -1) \
+            .to(torch.float32).contiguous()
+        n = rays.shape[0]
+        jitter = torch.rand(n, 1).to(dev).reshape(-1).contiguous() if is_train else None   # CPU draw, as :404-406
+        pts = torch.empty(n, S, 3, dtype=torch.float32, device=dev)
+        z = torch.empty(n, S, dtype=torch.float32, device=dev)
+        inside = torch.empty(n, S, dtype=torch.uint8, device=dev)
+        aabb = self._host_copy("_aabb_host", self.aabb)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().lrf_sample_ray(
+                _ptr(rays), _ptr(jitter), n, S, (C.c_float * 6)(*aabb), float(self.near_far[0]),
+                float(self.near_far[1]), float(self.stepSize), _ptr(pts), _ptr(z), _ptr(inside), _stream(dev)))
+        return pts, z, inside.bool()
 
 
 class TensorVMSplit(TensorBase):
@@ -726,17 +838,15 @@ class TensorVMSplit(TensorBase):
         return self.vectorDiffs(self.density_line) + self.vectorDiffs(self.app_line)
 
     def density_L1(self):
-        g = self.gridSize
-        n_vox = int(torch.prod(g))
-        feat = torch.zeros(n_vox, device=g.device)
-        for i in range(3):
-            plane = self.density_plane[i].reshape(-1, int(torch.prod(g[self.matMode[i]])))
-            line = self.density_line[i].reshape(-1, int(g[self.vecMode[i]]))
-            feat = feat + torch.bmm(plane[..., None], line[:, None]).view(-1, n_vox).sum(0)
-        return torch.sqrt(self.feature2density(feat).clamp(1e-5)).mean()
+        """tensoRF.py:83-92 -- streamed over the G^3 flat indices (differentiable, no dense intermediate)."""
+        _require_cuda(self.density_plane[0], "density_plane")
+        return _DensityL1Fn.apply(self, *self.density_plane, *self.density_line)
 
     def _tv(self, planes, lines, reg):
-        total = 0
+        if type(reg).__name__ == "TVLoss" and hasattr(reg, "TVLoss_weight") and planes[0].is_cuda:
+            coefs = [1e-2] * len(planes) + [1e-3] * len(lines)
+            return _TVFn.apply(float(reg.TVLoss_weight), coefs, *planes, *lines)
+        total = 0                                   # any other callable: the reference's formulation
         for p, l in zip(planes, lines):
             total = total + reg(p.transpose(0, 1)) * 1e-2 + reg(l.transpose(0, 1)) * 1e-3
         return total
@@ -750,13 +860,25 @@ class TensorVMSplit(TensorBase):
     # -- resolution schedule (tensoRF.py:198-233) --------------------------------------------------
     @torch.no_grad()
     def up_sampling_VM(self, plane_coef, line_coef, res_target):
+        """tensoRF.py:198-221 -- bilinear / align_corners=True resize, written channel-last directly by
+        lrf_upsample (CPU tensors, e.g. in host-only tests, go through F.interpolate)."""
+        lib = None
         for i, (vec_id, (m0, m1)) in enumerate(zip(self.vecMode, self.matMode)):
-            p = F.interpolate(plane_coef[i].detach(), size=(res_target[m1], res_target[m0]),
-                              mode="bilinear", align_corners=True)
-            l = F.interpolate(line_coef[i].detach(), size=(res_target[vec_id], 1),
-                              mode="bilinear", align_corners=True)
-            plane_coef[i] = torch.nn.Parameter(_cl(p))
-            line_coef[i] = torch.nn.Parameter(_cl(l))
+            for coef, (h2, w2) in ((plane_coef, (int(res_target[m1]), int(res_target[m0]))),
+                                   (line_coef, (int(res_target[vec_id]), 1))):
+                src = coef[i].detach()
+                if not src.is_cuda:
+                    coef[i] = torch.nn.Parameter(_cl(F.interpolate(src, size=(h2, w2), mode="bilinear",
+                                                                   align_corners=True)))
+                    continue
+                if not src.is_contiguous(memory_format=torch.channels_last) or src.shape[3] == 1:
+                    src = src.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)    # memory [H][W][C]
+                c, h, w = src.shape[1], src.shape[2], src.shape[3]
+                dst = _cl_empty(c, h2, w2, src.device)
+                lib = lib or _lib.lib()
+                with torch.cuda.device(src.device):
+                    _lib.check(lib.lrf_upsample(_ptr(src), h, w, _ptr(dst), h2, w2, c, _stream(src.device)))
+                coef[i] = torch.nn.Parameter(dst)
         return plane_coef, line_coef
 
     @torch.no_grad()

@@ -402,9 +402,65 @@ def gen_fullsize():
     save("cfg3_300", **arrays)
 
 
+# ---- G9: schedule-time operators and the AABB sampler, non-cubic grid ----------
+def gen_sched():
+    from utils.utils import TVLoss               # the reference's regulariser (utils/utils.py:293-312)
+    m = make_field([20, 24, 28], 50, density_shift=-7.5)
+    with torch.no_grad():
+        for p in list(m.density_plane) + list(m.density_line):
+            p.mul_(4.0)
+    arrays = field_to_dict(m)
+    # regularisers + their autograd gradients
+    reg = TVLoss()
+    for name, fn in (("l1", m.density_L1), ("tv_density", lambda: m.TV_loss_density(reg)),
+                     ("tv_app", lambda: m.TV_loss_app(reg))):
+        m.zero_grad()
+        val = fn()
+        val.backward()
+        arrays[f"{name}.value"] = val.detach().numpy()
+        for k, p_ in m.named_parameters():
+            if p_.grad is not None and float(p_.grad.abs().sum()) > 0:
+                arrays[f"{name}.grad.{k}"] = p_.grad.clone().numpy()
+    m.zero_grad()
+    # AABB sampler: eval and seeded train
+    rays = rays_cfg1(48, seed=51)
+    rays[:, :3] *= 8.0                            # origins in and around the [-2,2]^3 box
+    rays[0, 3] = 0.0                              # a zero direction component (the 1e-6 substitution)
+    arrays["sr.rays"] = rays.numpy()
+    with torch.no_grad():
+        pts, z, inside = m.sample_ray(rays[:, :3], rays[:, 3:], is_train=False, N_samples=40)
+        arrays["sr.eval.pts"], arrays["sr.eval.z"], arrays["sr.eval.inside"] = pts.numpy(), z.numpy(), inside.numpy()
+        torch.manual_seed(52)
+        pts, z, inside = m.sample_ray(rays[:, :3], rays[:, 3:], is_train=True, N_samples=-1)
+        arrays["sr.train.pts"], arrays["sr.train.z"], arrays["sr.train.inside"] = pts.numpy(), z.numpy(), inside.numpy()
+    # occupancy mask: dense alpha, mask, then dense alpha again with the mask in place
+    with torch.no_grad():
+        arrays["mask.alpha0"] = m.getDenseAlpha((10, 12, 14)).numpy()
+        quiet(m.updateAlphaMask, (10, 12, 14))
+        arrays["mask.volume"] = m.alphaMask.alpha_volume.numpy()
+        frac = float(m.alphaMask.alpha_volume.mean())
+        assert 0.05 < frac < 0.95, frac
+        arrays["mask.alpha1"] = m.getDenseAlpha((11, 9, 13)).numpy()
+        # pooled alpha before thresholding, to identify exact ties on alphaMask_thres in the test
+        a = arrays["mask.alpha0"]
+        pooled = torch.nn.functional.max_pool3d(torch.from_numpy(a).clamp(0, 1).transpose(0, 2).contiguous()[None, None],
+                                                kernel_size=3, padding=1, stride=1)[0, 0]
+        arrays["mask.pooled"] = pooled.numpy()
+    # upsampling
+    quiet(m.upsample_volume_grid, [30, 33, 41])
+    for k, v in m.state_dict().items():
+        if "plane" in k or "line" in k:
+            arrays["up." + k] = v.numpy()
+    arrays["up.nSamples"] = np.array(m.nSamples)
+    save("sched_nc", **arrays)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "fullsize":
         gen_fullsize()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "sched":
+        gen_sched()
         sys.exit(0)
     gen_cfg1()
     gen_aniso()
@@ -413,3 +469,4 @@ if __name__ == "__main__":
     gen_local()
     gen_grads()
     gen_fullsize()
+    gen_sched()
