@@ -470,6 +470,7 @@ def main():
         args.warmup = 3
 
     import localrf_b200 as L
+    torch.set_grad_enabled(False)               # inference bench: the fused eval path, like renderer.py's @torch.no_grad
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -21,6 +21,8 @@
 // The math is the one pinned by oracle/lrf_oracle.c::orc_field_backward against the reference's
 // autograd.  CUDA cores only; the tensor-core MLP backward is the next step.
 #include "../../include/localrf_b200.h"
+#include <cstdlib>
+
 #include "lrf_device.cuh"
 
 namespace lrf {
@@ -621,6 +623,10 @@ bwd_shade_kernel(const FieldDev F, const BwdArgs A) {
   }
 }
 
+}  // namespace lrf
+#include "lrf_backward_tc.cuh"   // DRAFT tensor-core variant of the shade step (LRF_BWD_TC=1), never run
+namespace lrf {
+
 // ====================================================================================================
 // 3. density branch + rays
 // ====================================================================================================
@@ -763,7 +769,11 @@ __global__ void prepare_backward_kernel(const float* __restrict__ basis, const f
 }
 
 // ---- host-side launchers --------------------------------------------------------------------------
-size_t backward_prepared_bytes() { return (size_t)BP_FLOATS * sizeof(float); }
+constexpr size_t BP_TC_OFFSET = ((size_t)BP_FLOATS * sizeof(float) + 1023) & ~(size_t)1023;   // forward operand block
+size_t backward_prepared_bytes() { return BP_TC_OFFSET + (size_t)PREP_BYTES; }
+cudaError_t launch_prepare(const float* basis, const float* w1, const float* b1, const float* w2,
+                           const float* b2, const float* w3, const float* b3, unsigned char* prep,
+                           cudaStream_t stream);
 size_t backward_scratch_bytes(long long n_rays, int S) {
   return bwd_scratch_layout(n_rays, S, nullptr, nullptr, nullptr);
 }
@@ -773,7 +783,9 @@ cudaError_t launch_prepare_backward(const float* basis, const float* w1, const f
                                     const float* w2, const float* b2, const float* w3,
                                     const float* b3, float* bp, cudaStream_t stream) {
   prepare_backward_kernel<<<64, 256, 0, stream>>>(basis, w1, b1, w2, b2, w3, b3, bp);
-  return cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return launch_prepare(basis, w1, b1, w2, b2, w3, b3, reinterpret_cast<unsigned char*>(bp) + BP_TC_OFFSET, stream);
 }
 
 cudaError_t launch_render_backward(const FieldDev& F, BwdArgs A, void* scratch, int n_sms,
@@ -800,7 +812,19 @@ cudaError_t launch_render_backward(const FieldDev& F, BwdArgs A, void* scratch, 
   bwd_march_kernel<<<grid, MARCH_THREADS, 0, stream>>>(F, A);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  bwd_shade_kernel<<<n_sms, SH_THREADS, smem, stream>>>(F, A);
+  static const bool use_tc = [] { const char* v = getenv("LRF_BWD_TC"); return v && v[0] == '1'; }();
+  if (use_tc) {
+    static bool configured_tc[64] = {false};
+    if (dev >= 0 && dev < 64 && !configured_tc[dev]) {
+      e = cudaFuncSetAttribute(bwd_shade_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total);
+      if (e != cudaSuccess) return e;
+      configured_tc[dev] = true;
+    }
+    bwd_shade_tc_kernel<<<n_sms, TC_THREADS, TcSmem::total, stream>>>(
+        F, A, reinterpret_cast<const unsigned char*>(A.bp) + BP_TC_OFFSET);
+  } else {
+    bwd_shade_kernel<<<n_sms, SH_THREADS, smem, stream>>>(F, A);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   bwd_density_kernel<<<grid, MARCH_THREADS, 0, stream>>>(F, A);

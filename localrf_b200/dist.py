@@ -140,3 +140,54 @@ def render_sharded(local_tensorfs, ray_ids, view_ids, W, H, group=None, exchange
     local_tensorfs(ray_ids[lo:hi], view_ids, W, H, exchange=(exchange, lo), **kw)
     full = exchange.gathered(n)
     return full[:, :3], full[:, 3]
+
+
+# ---- data-parallel training ("+ DP gradient all-reduce") ---------------------------
+def trainable_parameters(local_tensorfs):
+    """The tensors one optimisation step updates (local_tensorfs.py:193-290): the newest field's
+    parameters (rf_optimizer), the poses / exposures still linked to it, the intrinsics."""
+    lt = local_tensorfs
+    params = [p for g in lt.rf_optimizer.param_groups for p in g["params"]]
+    for i in lt._live_pose_ids():
+        params += [lt.r_c2w[i], lt.t_c2w[i], lt.exposure[i]]
+    params += [lt.focal_offset, lt.center_rel]
+    return [p for p in params if p.requires_grad]
+
+
+def allreduce_gradients(local_tensorfs, group=None, bucket_bytes=64 << 20):
+    """Averages the gradients of one training step over the ranks (each rank rendered its own shard of
+    the ray batch): flat buckets of <= bucket_bytes, one all-reduce each (NCCL over NVLink / NVSwitch;
+    NVLS reduces inside the switch when available).  A parameter without a gradient on this rank
+    contributes zeros (every rank must issue the same collectives).  Call between loss.backward() and
+    the optimiser steps; LocalTensorfs.optimizer_step does so when `dp_group` is set."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 0
+    views = []
+    for p in trainable_parameters(local_tensorfs):
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)              # preserves the parameter's memory format
+        g = p.grad
+        # a dense view of the gradient in its OWN memory order (no NCHW round trip for channel-last grids)
+        v = g.permute(0, 2, 3, 1) if (g.dim() == 4 and not g.is_contiguous()
+                                      and g.is_contiguous(memory_format=torch.channels_last)) else g
+        if not v.is_contiguous():
+            p.grad = g = g.contiguous()
+            v = g
+        views.append(v)
+    n_calls, lo = 0, 0
+    while lo < len(views):
+        hi, size = lo, 0
+        while hi < len(views) and (hi == lo or size + views[hi].numel() * 4 <= bucket_bytes):
+            size += views[hi].numel() * views[hi].element_size()
+            hi += 1
+        flat = torch.cat([v.reshape(-1) for v in views[lo:hi]])
+        dist.all_reduce(flat, group=group)
+        flat.div_(world)
+        off = 0
+        for v in views[lo:hi]:
+            v.copy_(flat[off:off + v.numel()].view(v.shape))      # writes through the view into p.grad
+            off += v.numel()
+        n_calls += 1
+        lo = hi
+    return n_calls

@@ -116,6 +116,7 @@ class LocalTensorfs(torch.nn.Module):
                 [self.focal_offset, self.center_rel], betas=(0.9, 0.99), lr=self.lr_i_init)
 
         # radiance fields
+        self.dp_group = None      # set to a process group (or True = WORLD) for data-parallel training
         self.tensorfs = torch.nn.ParameterList()
         self.rf_iter = []
         self.world2rf = torch.nn.ParameterList()
@@ -229,6 +230,9 @@ class LocalTensorfs(torch.nn.Module):
         self.rf_optimizer.zero_grad()
 
         loss.backward()
+        if getattr(self, "dp_group", None) is not None:     # data-parallel training: average the step's
+            from .dist import allreduce_gradients            # gradients over the ranks before any update
+            allreduce_gradients(self, None if self.dp_group is True else self.dp_group)
 
         self.rf_optimizer.step()
         if self.is_refining:

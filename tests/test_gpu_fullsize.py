@@ -113,7 +113,10 @@ def test_cfg3_three_fields_vs_reference_golden_and_oracle():
     bw = torch.tensor(g["blend"], device="cuda")
     ids = _frame_batch(int(g["batch"]))
     rgb, depth, _ = _render(lt, ids, world2rf=w2rf, blending_weights=bw)
-    n1, e1 = check_with_ties(rgb, g["rgb"], g["margin"], TOL, "cfg3 rgb vs reference")
+    # (a CPU run of the reference and a GPU run round exp() differently in the last bit often enough that
+    #  ~0.5 % of the rays per field sit on a flipped w > 1e-3 decision; against the reference on the SAME
+    #  GPU -- tests/test_gpu_vs_reference.py -- there are 0-1 such rays per batch)
+    n1, e1 = check_with_ties(rgb, g["rgb"], g["margin"], TOL, "cfg3 rgb vs reference", max_tie_frac=0.03)
     n2, e2 = check_with_ties(depth, g["depth"], g["margin"], TOL, "cfg3 depth vs reference")
     print(f"cfg3 vs reference: rgb worst {e1:.2e} ({n1} threshold ties), depth worst {e2:.2e}")
     assert n2 == 0
@@ -121,7 +124,7 @@ def test_cfg3_three_fields_vs_reference_golden_and_oracle():
     rgb, depth, _ = _render(lt, ids, world2rf=w2rf, blending_weights=bw)
     ref = oracle_local(lt, oracle_fields(lt), ids.cpu().numpy(), 0, 800, 800, world2rf=g["world2rf"],
                        blend=g["blend"])
-    n1, e1 = check_with_ties(rgb, ref["rgb"], ref["margin"], TOL, "cfg3 rgb vs oracle")
+    n1, e1 = check_with_ties(rgb, ref["rgb"], ref["margin"], TOL, "cfg3 rgb vs oracle", max_tie_frac=0.03)
     n2, e2 = check_with_ties(depth, ref["depth"], ref["margin"], TOL, "cfg3 depth vs oracle")
     print(f"cfg3 vs oracle: rgb worst {e1:.2e} ({n1} threshold ties), depth worst {e2:.2e}")
     assert n2 == 0
