@@ -241,6 +241,16 @@ int lrf_sample_ray(const float *rays, const float *jitter, int64_t N, int32_t S,
                    float near, float far, float step, float *pts, float *z, unsigned char *inside,
                    lrf_stream_t stream);
 
+/* Frame post-processing on the device.  replaces: the host-side conversions of renderer.py:126-131,173-176
+ * (rgb_map.cpu() ... cv2.imwrite(255 * rgb[..., ::-1]); visualize_depth -> cv2.applyColorMap, utils/utils.py:
+ * 179-197).  rgb [N] x 3 floats `rgb_stride` apart, depth [N] floats `depth_stride` apart (3 / 1, or 4 / 4 for the
+ * interleaved pix layout) -> rgb8 [N][3] 8-bit BGR and depth8 [N][3] = lut[(uint8)(255 * clip((d - d_lo) /
+ * (d_hi - d_lo + 1e-8), 0, 1))] with lut [256][3] (the caller's colour map, e.g. cv2.COLORMAP_JET).  Either
+ * output may be NULL.  Outputs may live in pinned host memory (zero-copy). */
+int lrf_frame_to_u8(const float *rgb, int32_t rgb_stride, const float *depth, int32_t depth_stride, int64_t N,
+                    float d_lo, float d_hi, const unsigned char *lut, unsigned char *rgb8, unsigned char *depth8,
+                    lrf_stream_t stream);
+
 /* [C][H][W] (contiguous NCHW parameter of the reference) -> [H][W][C] */
 int lrf_repack_nchw_to_nhwc(const float *src, float *dst, int32_t C, int32_t H, int32_t W,
                             lrf_stream_t stream);

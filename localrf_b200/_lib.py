@@ -77,7 +77,7 @@ EXPORTS = ["lrf_version", "lrf_sizeof", "lrf_last_error", "lrf_prepared_bytes", 
            "lrf_launch_info", "lrf_prepared_backward_bytes", "lrf_backward_scratch_bytes",
            "lrf_field_prepare_backward", "lrf_render_backward", "lrf_peer_barrier",
            "lrf_alpha_mask_build", "lrf_upsample", "lrf_density_l1", "lrf_density_l1_backward", "lrf_tv_sums",
-           "lrf_tv_sums_backward", "lrf_sample_ray"]
+           "lrf_tv_sums_backward", "lrf_sample_ray", "lrf_frame_to_u8"]
 
 
 def _stale():
@@ -160,6 +160,7 @@ def lib():
     L.lrf_tv_sums_backward.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_float, C.c_float, _vp, _vp]
     L.lrf_sample_ray.argtypes = [_vp, _vp, C.c_int64, C.c_int32, C.c_float * 6, C.c_float, C.c_float, C.c_float,
                                  _vp, _vp, _vp, _vp]
+    L.lrf_frame_to_u8.argtypes = [_vp, C.c_int32, _vp, C.c_int32, C.c_int64, C.c_float, C.c_float, _vp, _vp, _vp, _vp]
     L.lrf_peer_barrier.argtypes = [C.POINTER(_vp), C.c_int32, C.c_int32, C.c_uint64, _vp]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError if the header and the library ever drift apart

@@ -38,6 +38,9 @@ cudaError_t launch_sample_ray(const float* rays, const float* jitter, long long 
                               unsigned char* inside, int n_sms, cudaStream_t stream);
 cudaError_t launch_peer_barrier(unsigned long long* const* peer_flags, int rank, int world,
                                 unsigned long long seq, cudaStream_t stream);
+cudaError_t launch_frame_u8(const float* rgb, int rgb_stride, const float* depth, int depth_stride, long long N,
+                            float d_lo, float d_hi, const unsigned char* lut, unsigned char* rgb8,
+                            unsigned char* depth8, int n_sms, cudaStream_t stream);
 cudaError_t launch_app_products(const FieldDev& F, const float* xyz, long long M, float* out,
                                 cudaStream_t stream);
 cudaError_t launch_density_backward(const FieldDev& F, float* const* d_plane, float* const* d_line,
@@ -493,6 +496,21 @@ int lrf_sample_ray(const float* rays, const float* jitter, int64_t N, int32_t S,
   cudaError_t e = lrf::launch_sample_ray(rays, jitter, N, S, aabb, near, far, step, pts, z, inside, d.n_sms,
                                          (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "sample_ray_kernel");
+  return LRF_OK;
+}
+
+int lrf_frame_to_u8(const float* rgb, int32_t rgb_stride, const float* depth, int32_t depth_stride, int64_t N,
+                    float d_lo, float d_hi, const unsigned char* lut, unsigned char* rgb8, unsigned char* depth8,
+                    lrf_stream_t stream) {
+  if (N < 0) return fail(LRF_ERR_INVALID, "N < 0");
+  if (rgb8 && (!rgb || rgb_stride < 3)) return fail(LRF_ERR_INVALID, "rgb8 requested without rgb / stride >= 3");
+  if (depth8 && (!depth || depth_stride < 1 || !lut)) return fail(LRF_ERR_INVALID, "depth8 requested without depth / lut");
+  DevInfo d;
+  int rc = device_info(d);
+  if (rc != LRF_OK) return rc;
+  cudaError_t e = lrf::launch_frame_u8(rgb, rgb_stride, depth, depth_stride, N, d_lo, d_hi, lut, rgb8, depth8,
+                                       d.n_sms, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "frame_u8_kernel");
   return LRF_OK;
 }
 

@@ -308,6 +308,46 @@ __global__ void sample_ray_kernel(const float* __restrict__ rays, const float* _
   }
 }
 
+// ---- frame post-processing (renderer.py:126-131,173-176; utils/utils.py:179-197) -------------------------
+// rgb -> 8-bit BGR (what cv2.imwrite receives: 255 * rgb[..., ::-1], saturating round-to-nearest-even) and
+// depth -> colour-mapped 8-bit BGR through a 256-entry lookup table (cv2.applyColorMap of
+// (255 * clip((d - lo) / (hi - lo + 1e-8), 0, 1)).astype(uint8)); both are written where the caller points --
+// pinned host memory included, so a finished frame leaves the GPU as 6 bytes per pixel.
+__global__ void frame_u8_kernel(const float* __restrict__ rgb, int rgb_stride, const float* __restrict__ depth,
+                                int depth_stride, long long N, float d_lo, float d_hi,
+                                const unsigned char* __restrict__ lut, unsigned char* __restrict__ rgb8,
+                                unsigned char* __restrict__ depth8) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < N;
+       r += (long long)gridDim.x * blockDim.x) {
+    if (rgb8) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = __fmul_rn(255.0f, rgb[(long long)rgb_stride * r + c]);
+        rgb8[3 * r + (2 - c)] = (unsigned char)min(max(__float2int_rn(v), 0), 255);   // cv::saturate_cast<uchar>
+      }
+    }
+    if (depth8) {
+      float d = depth[(long long)depth_stride * r];
+      if (d != d) d = 0.0f;                                                     // np.nan_to_num
+      float x = __fdiv_rn(__fsub_rn(d, d_lo), __fadd_rn(__fsub_rn(d_hi, d_lo), 1e-8f));
+      x = fminf(fmaxf(x, 0.0f), 1.0f);
+      const int idx = (int)__fmul_rn(255.0f, x);                                // astype(uint8) truncates
+      depth8[3 * r] = lut[3 * idx]; depth8[3 * r + 1] = lut[3 * idx + 1]; depth8[3 * r + 2] = lut[3 * idx + 2];
+    }
+  }
+}
+
+cudaError_t launch_frame_u8(const float* rgb, int rgb_stride, const float* depth, int depth_stride, long long N,
+                            float d_lo, float d_hi, const unsigned char* lut, unsigned char* rgb8,
+                            unsigned char* depth8, int n_sms, cudaStream_t stream) {
+  if (N == 0) return cudaSuccess;
+  long long b = (N + 255) / 256;
+  if (b > (long long)n_sms * 16) b = (long long)n_sms * 16;
+  frame_u8_kernel<<<(unsigned)b, 256, 0, stream>>>(rgb, rgb_stride, depth, depth_stride, N, d_lo, d_hi, lut, rgb8,
+                                                  depth8);
+  return cudaGetLastError();
+}
+
 // ---- launchers -------------------------------------------------------------------------------------------
 static inline unsigned blocks_for(long long n, int threads, int n_sms) {
   long long b = (n + threads - 1) / threads;
