@@ -585,9 +585,9 @@ class LocalTensorfs(torch.nn.Module):
             key = (tuple(ids), tuple((id(t), t._version) for t in src), str(dev))
             cam2world = self._cached("c2w", key, lambda: self.get_cam2world(ids).detach()
                                      .to(dev, torch.float32).contiguous(), refs=src)
-            for i in set(ids):
-                guards.append((self.r_c2w, i, self.r_c2w[i], self.r_c2w[i]._version))
-                guards.append((self.t_c2w, i, self.t_c2w[i], self.t_c2w[i]._version))
+            for i in set(ids):     # (guards index the lists' _parameters dicts: ~10x cheaper than __getitem__)
+                guards.append((self.r_c2w._parameters, str(i), self.r_c2w[i], self.r_c2w[i]._version))
+                guards.append((self.t_c2w._parameters, str(i), self.t_c2w[i], self.t_c2w[i]._version))
         else:
             cam2world = cam2world.detach().to(dev, torch.float32).contiguous()
         fov360 = self.fov == 360
@@ -607,7 +607,7 @@ class LocalTensorfs(torch.nn.Module):
             key = (tuple(ids), bool(test_id), n_e, tuple((id(t), t._version) for t in src), str(dev))
             exposure = self._cached("expo", key, lambda: self._exposure_for(ids, test_id, dev), refs=src)
             for i, t in zip(used, src):
-                guards.append((self.exposure, i, t, t._version))
+                guards.append((self.exposure._parameters, str(i), t, t._version))
         rays_i = ray_ids.detach()
         if rays_i.dtype != torch.int64 or not rays_i.is_contiguous():
             rays_i = rays_i.to(torch.int64).contiguous()
@@ -675,8 +675,11 @@ class LocalTensorfs(torch.nn.Module):
                     if want_plan:
                         launches.append((rf, z, b))
                         keep.append(w2rf)
-                        guards.append((self.tensorfs, k, rf, None))
-                        guards.append((world2rf, k, w2, w2._version))
+                        guards.append((self.tensorfs._modules, str(k), rf, None))
+                        if isinstance(world2rf, torch.nn.ParameterList):
+                            guards.append((world2rf._parameters, str(k), w2, w2._version))
+                        else:
+                            guards.append((world2rf, k, w2, w2._version))
                         guards.append((rf.__dict__, "nSamples", rf.nSamples, "eq"))
             if exchange is not None:
                 exchange[0].close_step(stream)

@@ -501,11 +501,16 @@ class TensorBase(torch.nn.Module):
         only when a tensor it points at is replaced, the prepared block only when the MLP / basis
         weights change (data pointer or version counter) -- every optimiser step while training,
         never inside an eval loop."""
-        rm = self.renderModule
-        mlp = (self.basis_mat.weight, rm.mlp[0].weight, rm.mlp[0].bias, rm.mlp[2].weight,
-               rm.mlp[2].bias, rm.mlp_view[0].weight, rm.mlp_view[0].bias)
-        grids = tuple(self.density_plane) + tuple(self.density_line) + tuple(self.app_plane) + \
-            tuple(self.app_line)
+        # (read through the modules' _parameters / _modules dicts: ParameterList / Sequential indexing
+        #  costs ~1 us per access, and this runs on every render call)
+        mods = self._modules
+        rm = mods["renderModule"]._modules
+        l0, l2, l3 = rm["mlp"]._modules["0"]._parameters, rm["mlp"]._modules["2"]._parameters, \
+            rm["mlp_view"]._modules["0"]._parameters
+        mlp = (mods["basis_mat"]._parameters["weight"], l0["weight"], l0["bias"], l2["weight"], l2["bias"],
+               l3["weight"], l3["bias"])
+        grids = (*mods["density_plane"]._parameters.values(), *mods["density_line"]._parameters.values(),
+                 *mods["app_plane"]._parameters.values(), *mods["app_line"]._parameters.values())
         am = self.alphaMask
         k_struct = (tuple(t.data_ptr() for t in grids + mlp), z.data_ptr(), z.numel(),
                     None if am is None else (am.alpha_volume.data_ptr(), am.aabb._version),

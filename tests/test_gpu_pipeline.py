@@ -18,7 +18,9 @@ def test_pipeline_frames_match_direct_calls_and_host_conversions():
     W, H = 96, 80
     pipe = L.FramePipeline(lt, W, H, depth_minmax=(0.0, 5.0), n_buffers=3, keep_float=True)
     frames = [torch.tensor([f], device="cuda") for f in (0, 5, 6, 7, 8, 30, 63)]
-    got = list(pipe.render(frames, floater_thresh=0.5))
+    # the yielded arrays are views of the ring's pinned buffers (valid until n_buffers more submits): copy
+    got = [{k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in fr.items()}
+           for fr in pipe.render(frames, floater_thresh=0.5)]
     assert len(got) == len(frames) and pipe.in_flight() == 0
     ids = torch.arange(W * H, dtype=torch.int64, device="cuda")
     for view, fr in zip(frames, got):
