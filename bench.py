@@ -457,6 +457,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "distB", "incoherent", "cfg3", "cfg5"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong", "frame"])
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
+    ap.add_argument("--lag", type=int, default=1, help="fused exchange: steps the consumer of the gathered "
+                    "pixels runs behind (1 = double-buffered, 0 = same-step barrier)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--grid", type=int, default=None)
@@ -506,8 +508,9 @@ def main():
         exchange_kind = args.exchange
         if args.exchange == "fused":
             try:
-                xch = PixelExchange(rays_per_step_global, device=dev)
-                exchange_kind = "fused (multimem stores)" if xch.mc_ptr else "fused (peer stores)"
+                xch = PixelExchange(rays_per_step_global, device=dev, lag=args.lag)
+                exchange_kind = ("fused (multimem stores)" if xch.mc_ptr else "fused (peer stores)") + \
+                    f", consumer lag {args.lag} step(s)"
             except Exception as e:
                 print(f"bench: symmetric memory unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
                 exchange_kind = "nccl (fused unavailable)"
@@ -569,6 +572,25 @@ def main():
     value = rays_per_step_global * args.steps / (total_ms * 1e-3)
     launches = [len(p.launches) for p in lt.__dict__.get("_plans", {}).values()]
     gpu_launches = args.steps * (max(launches) if launches else 1) + (args.steps if xch is not None else 0)
+
+    # N > 1: what a step costs on each rank without any exchange (per-rank events, max over ranks): separates
+    # the kernel from the exchange / rank-desynchronisation share of ms_per_step
+    ms_no_exchange = None
+    if world > 1:
+        k = max(args.steps // 2, 8)
+        evx = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        dist.barrier(); torch.cuda.synchronize()
+        for i in range(k):
+            flush.zero_(); flush.zero_()
+            bi = batch_index(args.warmup + i)
+            lo, hi, _ = shard_of(ids_dev[bi].shape[0])
+            evx[i][0].record()
+            lt(ids_dev[bi][lo:hi], views_dev[id(views_host[bi])], IMG_W, IMG_H, **kw)
+            evx[i][1].record()
+        torch.cuda.synchronize()
+        t = torch.tensor([sum(a.elapsed_time(c) for a, c in evx) / k], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_no_exchange = float(t)
 
     # roofline of the fused kernel (this rank's launches; N=1 only: with N>1 the events also cover the exchange)
     peak, peak_src = peaks()
@@ -693,6 +715,7 @@ def main():
                                 "strong": "each 4096-ray batch split over the ranks (BASELINE config 4)",
                                 "frame": "the frame's 640000 rays split over the ranks, one exchange per frame"}[scaling],
                    "exchange": exchange_kind,
+                   "ms_per_step_without_exchange": ms_no_exchange,
                    "parallelism": f"ray-batch data parallel x{world}"},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

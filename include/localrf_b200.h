@@ -207,6 +207,11 @@ int lrf_render_backward(const LrfField *field, const void *prepared_bwd, const f
  * one per step, starting at 1 (flags zero-initialised).  replaces: the ncclAllGather of SURVEY.md 8e. */
 int lrf_peer_barrier(unsigned long long *const *peer_flags, int32_t rank, int32_t world,
                      unsigned long long seq, lrf_stream_t stream);
+/* The same with the two halves decoupled: signals `seq`, waits until every peer has signalled `wait_seq`
+ * (<= seq).  wait_seq = seq - 1 is the double-buffered exchange: step i's pixels are pushed while the
+ * consumer works on step i-1's, so a step never waits for the slowest peer of the SAME step. */
+int lrf_peer_signal_wait(unsigned long long *const *peer_flags, int32_t rank, int32_t world,
+                         unsigned long long seq, unsigned long long wait_seq, lrf_stream_t stream);
 
 /* ---- schedule-time operators on the field's tensors ---------------------------
  * Occupancy-mask rebuild.  replaces: getDenseAlpha + updateAlphaMask (models/tensorBase.py:501-536), which

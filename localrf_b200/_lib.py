@@ -75,7 +75,7 @@ EXPORTS = ["lrf_version", "lrf_sizeof", "lrf_last_error", "lrf_prepared_bytes", 
            "lrf_render", "lrf_mlp_forward", "lrf_app_products", "lrf_density_feature_backward",
            "lrf_app_products_backward", "lrf_density_feature", "lrf_app_feature", "lrf_repack_nchw_to_nhwc",
            "lrf_launch_info", "lrf_prepared_backward_bytes", "lrf_backward_scratch_bytes",
-           "lrf_field_prepare_backward", "lrf_render_backward", "lrf_peer_barrier",
+           "lrf_field_prepare_backward", "lrf_render_backward", "lrf_peer_barrier", "lrf_peer_signal_wait",
            "lrf_alpha_mask_build", "lrf_upsample", "lrf_density_l1", "lrf_density_l1_backward", "lrf_tv_sums",
            "lrf_tv_sums_backward", "lrf_sample_ray", "lrf_frame_to_u8"]
 
@@ -162,6 +162,7 @@ def lib():
                                  _vp, _vp, _vp, _vp]
     L.lrf_frame_to_u8.argtypes = [_vp, C.c_int32, _vp, C.c_int32, C.c_int64, C.c_float, C.c_float, _vp, _vp, _vp, _vp]
     L.lrf_peer_barrier.argtypes = [C.POINTER(_vp), C.c_int32, C.c_int32, C.c_uint64, _vp]
+    L.lrf_peer_signal_wait.argtypes = [C.POINTER(_vp), C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, _vp]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError if the header and the library ever drift apart
     _lib = L

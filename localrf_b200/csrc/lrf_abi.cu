@@ -37,7 +37,7 @@ cudaError_t launch_sample_ray(const float* rays, const float* jitter, long long 
                               float near, float far, float step, float* pts, float* z,
                               unsigned char* inside, int n_sms, cudaStream_t stream);
 cudaError_t launch_peer_barrier(unsigned long long* const* peer_flags, int rank, int world,
-                                unsigned long long seq, cudaStream_t stream);
+                                unsigned long long seq, unsigned long long wait_seq, cudaStream_t stream);
 cudaError_t launch_frame_u8(const float* rgb, int rgb_stride, const float* depth, int depth_stride, long long N,
                             float d_lo, float d_hi, const unsigned char* lut, unsigned char* rgb8,
                             unsigned char* depth8, int n_sms, cudaStream_t stream);
@@ -516,12 +516,18 @@ int lrf_frame_to_u8(const float* rgb, int32_t rgb_stride, const float* depth, in
 
 int lrf_peer_barrier(unsigned long long* const* peer_flags, int32_t rank, int32_t world,
                      unsigned long long seq, lrf_stream_t stream) {
+  return lrf_peer_signal_wait(peer_flags, rank, world, seq, seq, stream);
+}
+
+int lrf_peer_signal_wait(unsigned long long* const* peer_flags, int32_t rank, int32_t world,
+                         unsigned long long seq, unsigned long long wait_seq, lrf_stream_t stream) {
+  if (wait_seq > seq) return fail(LRF_ERR_INVALID, "wait_seq must not exceed seq (a rank cannot wait for a step it has not signalled)");
   if (!peer_flags || world < 1 || world > LRF_MAX_PEERS || rank < 0 || rank >= world)
     return fail(LRF_ERR_INVALID, "bad peer_flags / rank / world");
   for (int p = 0; p < world; ++p)
     if (!peer_flags[p] || ((uintptr_t)peer_flags[p] & 7))
       return fail(LRF_ERR_INVALID, "peer flag arrays must be non-NULL and 8-byte aligned");
-  cudaError_t e = lrf::launch_peer_barrier(peer_flags, rank, world, seq, (cudaStream_t)stream);
+  cudaError_t e = lrf::launch_peer_barrier(peer_flags, rank, world, seq, wait_seq, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "peer_barrier_kernel");
   return LRF_OK;
 }

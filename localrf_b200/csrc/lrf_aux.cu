@@ -325,7 +325,7 @@ cudaError_t launch_repack(const float* src, float* dst, int C, long long HW, cud
 struct PeerFlags { unsigned long long* p[16]; };
 
 __global__ void peer_barrier_kernel(const PeerFlags F, const int rank, const int world,
-                                    const unsigned long long seq) {
+                                    const unsigned long long seq, const unsigned long long wait_seq) {
   const int t = threadIdx.x;
   if (t >= world) return;
   // the render kernel before us on this stream stored pixels into the peers' buffers: order those
@@ -337,14 +337,14 @@ __global__ void peer_barrier_kernel(const PeerFlags F, const int rank, const int
   unsigned long long v = 0;
   do {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(local) : "memory");
-  } while (v < seq);
+  } while (v < wait_seq);
 }
 
 cudaError_t launch_peer_barrier(unsigned long long* const* peer_flags, int rank, int world,
-                                unsigned long long seq, cudaStream_t stream) {
+                                unsigned long long seq, unsigned long long wait_seq, cudaStream_t stream) {
   PeerFlags F;
   for (int p = 0; p < 16; ++p) F.p[p] = p < world ? peer_flags[p] : nullptr;
-  peer_barrier_kernel<<<1, 32, 0, stream>>>(F, rank, world, seq);
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(F, rank, world, seq, wait_seq);
   return cudaGetLastError();
 }
 

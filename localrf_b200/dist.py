@@ -68,13 +68,18 @@ def gather_pixels(rgb, depth, n_total, group=None):
 class PixelExchange:
     """Gathered pixel buffer in symmetric memory + the step barrier (fused pixel exchange).
 
-    Two [max_rays, 4] buffers alternate between steps: a rank may already be storing step i+1 into its
-    peers while they still read step i; it cannot reach step i+2 before every peer has passed the
-    barrier of step i+1, which in the peer's stream order comes after its reads of step i.
+    `lag` = how many steps the consumer runs behind the producers.  lag 0 (render_sharded): closing step i
+    waits until every peer has pushed step i.  lag 1 (a renderer's steady state): closing step i pushes
+    the flag of step i and waits for step i-1 only, which the peers finished a whole step ago -- no rank
+    ever waits for the slowest peer of the same step; `gathered()` then returns step i-1.
+    2 (lag + 1) buffers of [max_rays, 4] rotate.  Why that many: a rank stores step s into the buffer
+    step s - 2(lag+1) used; before launching step s it has waited (closing step s-1) for every peer's
+    signal of step s-1-lag, and a peer issues that signal only after -- in its stream order -- it has
+    consumed the gathered pixels of step s-2-2lag, the previous occupant of the buffer.
     """
     FLAG_BYTES = 16 * 8
 
-    def __init__(self, max_rays, group=None, device=None, use_multicast=True):
+    def __init__(self, max_rays, group=None, device=None, use_multicast=True, lag=0):
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         self.group = group if group is not None else dist.group.WORLD
@@ -84,7 +89,9 @@ class PixelExchange:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.max_rays = int(max_rays)
         self.buf_bytes = (self.max_rays * 16 + 255) // 256 * 256
-        total = 2 * self.buf_bytes + self.FLAG_BYTES
+        self.lag = int(lag)
+        self.n_buf = 2 * (self.lag + 1)
+        total = self.n_buf * self.buf_bytes + self.FLAG_BYTES
         self.mem = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
         self.mem.zero_()
         torch.cuda.synchronize(self.device)
@@ -99,27 +106,28 @@ class PixelExchange:
                 mc = 0
         self.mc_ptr = mc
         self.seq = 0
-        self._flag_ptrs = (C.c_void_p * self.world)(*[p + 2 * self.buf_bytes for p in self.ptrs])
+        self._flag_ptrs = (C.c_void_p * self.world)(*[p + self.n_buf * self.buf_bytes for p in self.ptrs])
         self._lib = _lib
         dist.barrier(self.group)          # every rank has zeroed + mapped before anybody stores
 
     def fill_outputs(self, o, ray_lo):
         """Points an LrfOutputs at the NEXT step's buffer: peer p receives this rank's rays at row
         `ray_lo` of its gathered buffer."""
-        off = ((self.seq + 1) & 1) * self.buf_bytes + ray_lo * 16
+        off = ((self.seq + 1) % self.n_buf) * self.buf_bytes + ray_lo * 16
         o.n_peers = self.world
         for p in range(self.world):
             o.peer_pix[p] = self.ptrs[p] + off
         o.mc_pix = (self.mc_ptr + off) if self.mc_ptr else None
 
     def close_step(self, stream):
-        """Enqueues the barrier; afterwards `gathered(n)` holds every rank's pixels of this step."""
+        """Enqueues signal(step) + wait(step - lag); afterwards `gathered(n)` holds every rank's pixels of
+        step (this - lag)."""
         self.seq += 1
-        self._lib.check(self._lib.lib().lrf_peer_barrier(self._flag_ptrs, self.rank, self.world,
-                                                         self.seq, stream))
+        self._lib.check(self._lib.lib().lrf_peer_signal_wait(self._flag_ptrs, self.rank, self.world, self.seq,
+                                                             max(self.seq - self.lag, 0), stream))
 
     def gathered(self, n_rays):
-        off = (self.seq & 1) * self.buf_bytes
+        off = (max(self.seq - self.lag, 0) % self.n_buf) * self.buf_bytes
         return self.mem[off:off + n_rays * 16].view(torch.float32).view(n_rays, 4)
 
 
