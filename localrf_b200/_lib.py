@@ -92,7 +92,8 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    extra = os.environ.get("LRF_NVCC_EXTRA", "").split()          # tuning experiments (e.g. -DLRF_THREADS=640)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)  # the image's CC points at a gcc without libgomp
     r = subprocess.run(cmd, cwd=_CSRC, capture_output=True, text=True, env=env)

@@ -19,7 +19,9 @@
 //                       vector reductions); finishes d(rays) (vd = d/|d|, depth = sum(w z)/|d|).
 //
 // The math is the one pinned by oracle/lrf_oracle.c::orc_field_backward against the reference's
-// autograd.  CUDA cores only; the tensor-core MLP backward is the next step.
+// autograd.  The shade step has two implementations: bwd_shade_tc_kernel (lrf_backward_tc.cuh, the six
+// matrix products on tcgen05 with bf16 hi/lo operands and TMEM-resident weight gradients; default) and
+// bwd_shade_kernel below (fp32 on the CUDA cores, LRF_BWD_TC=0).
 #include "../../include/localrf_b200.h"
 #include <cstdlib>
 
@@ -624,7 +626,7 @@ bwd_shade_kernel(const FieldDev F, const BwdArgs A) {
 }
 
 }  // namespace lrf
-#include "lrf_backward_tc.cuh"   // DRAFT tensor-core variant of the shade step (LRF_BWD_TC=1), never run
+#include "lrf_backward_tc.cuh"   // tensor-core shade step (the default; LRF_BWD_TC=0 selects bwd_shade_kernel)
 namespace lrf {
 
 // ====================================================================================================
@@ -812,7 +814,10 @@ cudaError_t launch_render_backward(const FieldDev& F, BwdArgs A, void* scratch, 
   bwd_march_kernel<<<grid, MARCH_THREADS, 0, stream>>>(F, A);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  static const bool use_tc = [] { const char* v = getenv("LRF_BWD_TC"); return v && v[0] == '1'; }();
+  // tcgen05 shade step by default; LRF_BWD_TC=0 keeps the CUDA-core kernel (the independent fp32
+  // implementation the tensor-core one is tested against).  Read per call so tests can switch.
+  const char* tc_env = getenv("LRF_BWD_TC");
+  const bool use_tc = !(tc_env && tc_env[0] == '0');
   if (use_tc) {
     static bool configured_tc[64] = {false};
     if (dev >= 0 && dev < 64 && !configured_tc[dev]) {

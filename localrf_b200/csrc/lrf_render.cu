@@ -35,10 +35,14 @@
 
 namespace lrf {
 
-constexpr int THREADS = 512;
+#ifndef LRF_THREADS
+#define LRF_THREADS 512             // 16 warps (128 registers each); 640 = 20 warps at 96 registers
+#endif
+constexpr int THREADS = LRF_THREADS;
 constexpr int W_ISSUE = 8;          // warp 8: MMA issuer
-constexpr int W_CONS = 12;          // warps 12..15: consumers (warp % 4 = TMEM lane quarter)
-constexpr int MAX_PROD = 11;        // producer warps: 0..7 and 9..11
+constexpr int W_CONS = THREADS / 32 - 4;   // the last four warps: consumers (warp % 4 = TMEM lane quarter)
+constexpr int MAX_PROD = W_CONS - 1;       // producer warps: every other warp (11 at 512 threads)
+static_assert(THREADS % 128 == 0 && W_CONS > W_ISSUE + 1, "warp roles");
 constexpr int NSLOT = 3;            // ray slots per producer warp
 constexpr int QCAP = 64;            // per-warp queue of selected samples
 constexpr int SPIN_PAD = 2048;      // polls before a blocked producer pads the open tile

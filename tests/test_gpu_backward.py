@@ -43,9 +43,13 @@ def _grads(m, rays, z, c_rgb, c_depth, white_bg):
 @pytest.mark.parametrize("name,white_bg", [("cfg1_64", True), ("cfg1_64", False), ("relu_32", True),
                                            ("alphamask_32", True), ("opaque_32", False),
                                            ("grads_field", True)])
-def test_fused_backward_vs_oracle(name, white_bg, monkeypatch):
+@pytest.mark.parametrize("shade", ["tcgen05", "cuda_cores"])
+def test_fused_backward_vs_oracle(name, white_bg, shade, monkeypatch):
+    """Every gradient of lrf_render_backward against the oracle's analytic backward (pinned to the
+    reference's autograd), with the shade step on the tensor cores (default) and on the CUDA cores."""
     from gpu_helpers import module_from_golden
     from oracle import oracle as orc
+    monkeypatch.setenv("LRF_BWD_TC", "1" if shade == "tcgen05" else "0")
     g = load_golden(name)
     m = module_from_golden(g)
     _no_composed(m, monkeypatch)
@@ -89,7 +93,8 @@ def _l2_err(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def test_fused_backward_matches_composed_path_fullsize(field300, monkeypatch):
+@pytest.mark.parametrize("shade", ["tcgen05", "cuda_cores"])
+def test_fused_backward_matches_composed_path_fullsize(field300, monkeypatch, shade):
     """4096 rays at 300^3 / S = 344: every parameter gradient and d(rays) of the fused backward
     against autograd through the composed path (CUDA lookups + torch ops) on the same inputs -- a
     check for scale-related faults (indexing, tiles, scratch layout); the tight parity bars are the
@@ -105,7 +110,17 @@ def test_fused_backward_matches_composed_path_fullsize(field300, monkeypatch):
     the threshold at 0 (nothing to switch in (1)) the density grids and the dense MLP tensors must
     agree tightly and the appearance grids / rays to the size of one switched sample; at the default
     threshold the outputs agree except on the affected rays and every gradient stays within the size
-    of a few switched samples.  A real fault shows up as O(1) in these metrics."""
+    of a few switched samples.  A real fault shows up as O(1) in these metrics.
+
+    Both shade kernels are checked.  The tensor-core one evaluates the MLP exactly like the fused FORWARD
+    (three bf16 products of hi/lo-split operands, ~16 mantissa bits), so its ReLU decisions are those of
+    the forward that actually ran but differ from the composed path's fp32 torch MLP for pre-activations
+    within ~1e-5 of zero -- about 100x more switched units than between two fp32 implementations; the
+    dense MLP tensors then agree to a few 1e-4 of their scale (measured: mlp.2 4.7e-4, mlp.0.bias 2.2e-4,
+    mlp.0.weight 5.3e-4, basis 1.4e-3) instead of 5e-5.  The tight bars (2e-4 on every tensor) are the
+    oracle / reference-autograd goldens, which both kernels pass."""
+    monkeypatch.setenv("LRF_BWD_TC", "1" if shade == "tcgen05" else "0")
+    tc = shade == "tcgen05"
     m = field300
     rays = _batch_rays(4096, 5)
     z = m.sample_table(True, -1, rays.device)
@@ -142,9 +157,10 @@ def test_fused_backward_matches_composed_path_fullsize(field300, monkeypatch):
     for key, e in errs.items():
         if key.startswith("density_") or key.startswith("renderModule.mlp.2") or "mlp_view" in key \
                 or key == "renderModule.mlp.0.bias":
-            assert e < TOL, (key, e)                   # measured <= 5e-5
+            dense_ok = key.startswith("density_") or "mlp_view" in key or not tc
+            assert e < (TOL if dense_ok else 1e-3), (key, e)   # measured <= 5e-5 (tcgen05 MLP tensors: <= 4.7e-4)
         elif key in ("renderModule.mlp.0.weight", "basis_mat.weight"):
-            assert e < 1.5e-3, (key, e)                # measured 1e-4 / 2.5e-4
+            assert e < (3e-3 if tc else 1.5e-3), (key, e)      # measured 1e-4 / 2.5e-4 (tcgen05: 5.3e-4 / 1.4e-3)
         else:
             assert e < 2e-2, (key, e)                  # app grids, rays: measured 2e-3 / 3e-3
 
