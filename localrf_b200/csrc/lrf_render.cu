@@ -38,11 +38,16 @@ namespace lrf {
 #ifndef LRF_THREADS
 #define LRF_THREADS 512             // 16 warps (128 registers each); 640 = 20 warps at 96 registers
 #endif
+#ifndef LRF_CONS_WARPS
+#define LRF_CONS_WARPS 4            // 4: one consumer warp per TMEM lane quarter; 8: two per quarter (64 columns each)
+#endif
 constexpr int THREADS = LRF_THREADS;
-constexpr int W_ISSUE = 8;          // warp 8: MMA issuer
-constexpr int W_CONS = THREADS / 32 - 4;   // the last four warps: consumers (warp % 4 = TMEM lane quarter)
-constexpr int MAX_PROD = W_CONS - 1;       // producer warps: every other warp (11 at 512 threads)
-static_assert(THREADS % 128 == 0 && W_CONS > W_ISSUE + 1, "warp roles");
+constexpr int N_CONS = LRF_CONS_WARPS;
+constexpr int W_CONS = THREADS / 32 - N_CONS;   // the last warps: consumers (warp % 4 = TMEM lane quarter)
+constexpr int W_ISSUE = W_CONS - 1;             // the warp before them: MMA issuer
+constexpr int MAX_PROD = W_ISSUE;               // producer warps 0 .. W_ISSUE-1 (11 at 512 threads / 4 consumers)
+constexpr int CONS_COLS = FC * 4 / N_CONS;      // columns of the accumulators one consumer thread handles
+static_assert(THREADS % 128 == 0 && W_ISSUE >= 1 && (N_CONS == 4 || N_CONS == 8), "warp roles");
 constexpr int NSLOT = 3;            // ray slots per producer warp
 constexpr int QCAP = 64;            // per-warp queue of selected samples
 constexpr int SPIN_PAD = 2048;      // polls before a blocked producer pads the open tile
@@ -76,7 +81,7 @@ struct Ctrl {                       // CTA control block in shared memory
 };
 
 struct SmemV3 {
-  int prep, a1, mslot, mw, slots, q, alpha, z, ctrl, total;
+  int prep, a1, mslot, mw, part, slots, q, alpha, z, ctrl, total;
   int per_prod;                     // bytes of one producer's queue (+ alpha table)
 };
 
@@ -89,6 +94,7 @@ __host__ __device__ inline SmemV3 smem_v3(int S, bool floater, int nprod) {
   L.a1 = off;     off += 2 * 2 * OPER1_BYTES;          // two A1 tiles (hi + lo each)
   L.mslot = off;  off += 2 * TM;                        // per-row slot id (u8), two tiles
   L.mw = off;     off += 2 * TM * 4;                    // per-row weight
+  L.part = off;   off += (N_CONS == 8 ? TM * 4 * 4 : 0); // layer-3 partial sums of the upper column half
   off = (off + 15) & ~15;
   L.slots = off;  off += MAX_PROD * NSLOT * (int)sizeof(Slot);
   L.q = off;
@@ -202,7 +208,12 @@ struct ProdCtx {
 // can be more than two tiles ahead of the consumers, which a 1-bit phase cannot express.
 __device__ __forceinline__ void wait_tile_free(Ctrl* ctrl, unsigned int T) {
   if (T >= 2) {
-    while (*reinterpret_cast<volatile unsigned int*>(&ctrl->released) + 1u < T) { }
+#ifndef LRF_SPIN_NS
+#define LRF_SPIN_NS 0
+#endif
+    while (*reinterpret_cast<volatile unsigned int*>(&ctrl->released) + 1u < T) {
+      if (LRF_SPIN_NS) __nanosleep(LRF_SPIN_NS);   // back off: a spinning producer takes issue slots from the gathers
+    }
     __threadfence_block();
   }
 }
@@ -304,7 +315,7 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
     mbar_init(smem_u32(&ctrl->full[0]), TM);
     mbar_init(smem_u32(&ctrl->full[1]), TM);
     mbar_init(smem_u32(&ctrl->mma1), 1);
-    mbar_init(smem_u32(&ctrl->a2rdy), TM);
+    mbar_init(smem_u32(&ctrl->a2rdy), TM * N_CONS / 4);
     mbar_init(smem_u32(&ctrl->mma2), 1);
     ctrl->cursor = 0; ctrl->prod_done = 0; ctrl->n_tiles_final = 0; ctrl->done = 0;
     ctrl->released = 0;
@@ -333,7 +344,7 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&ctrl->tmem);
 
-  const int prod_id = warp < W_ISSUE ? warp : (warp > W_ISSUE && warp < W_CONS ? warp - 1 : -1);
+  const int prod_id = warp < W_ISSUE ? warp : -1;
 
   if (prod_id >= 0 && prod_id < nprod) {
     // ======================================= PRODUCER ============================================
@@ -507,6 +518,8 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
   } else if (warp >= W_CONS) {
     // ======================================= CONSUMERS ===========================================
     const int q4 = warp & 3, row = q4 * 32 + lane, ctid = tid - W_CONS * 32;
+    const int chalf = (warp - W_CONS) >> 2, col0 = chalf * CONS_COLS;     // this thread's accumulator columns
+    float* part_s = reinterpret_cast<float*>(smem + L.part);
     const uint32_t t_row = tmem + ((uint32_t)(q4 * 32) << 16);
     const float* tail = reinterpret_cast<const float*>(smem + L.prep + PREP_TAIL);
     const float* b1_s = tail + TAIL_B1;
@@ -526,14 +539,14 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
       // row metadata -> registers, then the A1 tile (and its metadata) may be rewritten
       const int my_slot = smem[L.mslot + b * TM + row];
       const float my_w = reinterpret_cast<const float*>(smem + L.mw)[b * TM + row];
-      asm volatile("bar.sync 2, 128;" ::: "memory");   // MMA1(T) done + all metadata read ->
+      asm volatile("bar.sync 2, %0;" ::"n"(N_CONS * 32) : "memory");   // MMA1(T) done + all metadata read ->
       if (ctid == 0) {                                  // the A1 buffer of tile T is free again
         __threadfence_block();
         *reinterpret_cast<volatile unsigned int*>(&ctrl->released) = T + 1u;
       }
       // -- epilogue 1: h1 = relu(acc1 + b1) -> bf16 hi/lo, layer 2's A operand in TMEM -------------
 #pragma unroll 1
-      for (int c0 = 0; c0 < FC; c0 += 32) {
+      for (int c0 = col0; c0 < col0 + CONS_COLS; c0 += 32) {
         float v[32];
         tmem_ld32(t_row + (uint32_t)(TM_ACC1 + c0), v);
         uint32_t hi[16], lo[16];
@@ -555,7 +568,7 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
       tc_fence_after();
       float pa[3] = {0.0f, 0.0f, 0.0f}, pb[3] = {0.0f, 0.0f, 0.0f};   // two chains per channel (ILP)
 #pragma unroll 1
-      for (int c0 = 0; c0 < FC; c0 += 32) {
+      for (int c0 = col0; c0 < col0 + CONS_COLS; c0 += 32) {
         float v[32];
         tmem_ld32(t_row + (uint32_t)(TM_ACC2 + c0), v);
 #pragma unroll
@@ -572,8 +585,19 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
         }
       }
       tc_fence_before();
+      if (N_CONS == 8) {                     // the two column halves of a row meet through shared memory
+        if (chalf == 1) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) part_s[row * 4 + c] = pa[c] + pb[c];
+        }
+        asm volatile("bar.sync 3, %0;" ::"n"(N_CONS * 32) : "memory");
+        if (chalf == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { pa[c] += pb[c]; pb[c] = part_s[row * 4 + c]; }
+        }
+      }
       // -- composite (tensorBase.py:632): w * rgb into the ray's fixed-point accumulators -------------
-      if (my_slot != 0xFF) {
+      if (my_slot != 0xFF && chalf == 0) {
         Slot* sl = slots + my_slot;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
