@@ -209,7 +209,7 @@ struct ProdCtx {
 __device__ __forceinline__ void wait_tile_free(Ctrl* ctrl, unsigned int T) {
   if (T >= 2) {
 #ifndef LRF_SPIN_NS
-#define LRF_SPIN_NS 0
+#define LRF_SPIN_NS 200
 #endif
     while (*reinterpret_cast<volatile unsigned int*>(&ctrl->released) + 1u < T) {
       if (LRF_SPIN_NS) __nanosleep(LRF_SPIN_NS);   // back off: a spinning producer takes issue slots from the gathers
