@@ -60,6 +60,8 @@ constexpr float FIX_SCALE = 1073741824.0f;              // 2^30
 constexpr float FIX_INV = 1.0f / 1073741824.0f;
 
 struct Slot {                       // one ray in flight between a producer and the consumers
+  float o[3];                       // ray origin / |d| (the gathers of queued samples read the ray from its slot)
+  float nrm;
   float vd[3];
   float blend;
   unsigned int rgb[3];              // sum of w * rgb, fixed point
@@ -70,18 +72,39 @@ struct Slot {                       // one ray in flight between a producer and 
   int state;                        // 0 free, 1 active
 };
 
+#ifndef LRF_STEAL
+#define LRF_STEAL 1                 // idle producers help the in-flight rays of their CTA, one 32-sample step at a time
+#endif
+constexpr int MAXST = 32;           // steps a ray may have for step stealing (S <= 1024); longer rays march sequentially
+
+// One ray being marched by its owner producer and, once the global ray queue is empty, by the idle
+// producers of the CTA: steps are claimed from `next_step`; step s publishes the product P[s] of its
+// 32 transmittance factors right after its density gathers, then waits for P[0..s-1] and multiplies
+// them IN ORDER (bit-identical to the sequential carry), so every weight is independent of who
+// computed which step; per-step partial sums are added in step order by the owner.
+struct RayRec {
+  unsigned int next_step;           // claim counter (>= n_steps between rays: nothing to claim)
+  unsigned int stop_at;             // steps >= stop_at contribute nothing (early ray termination, T < 1e-10)
+  unsigned int ready, done;         // bit s: P[s] published / step s finished (sums stored, selected samples counted)
+  int slot_id;
+  long long ray;
+  float P[MAXST], accs[MAXST], deps[MAXST];
+  int marched[MAXST];
+};
+
 struct Ctrl {                       // CTA control block in shared memory
   unsigned long long bar_w, full[2], mma1, a2rdy, mma2;
   uint32_t tmem;
   unsigned int released;            // tiles whose A1 buffer + row metadata may be overwritten
   unsigned int cursor;              // rows handed out so far (tile = cursor >> 7)
   unsigned int prod_done;
+  unsigned int draw_done;           // producers whose draw from the global ray queue has failed (they help from then on)
   unsigned int n_tiles_final;
   unsigned int done;
 };
 
 struct SmemV3 {
-  int prep, a1, mslot, mw, part, slots, q, alpha, z, ctrl, total;
+  int prep, a1, mslot, mw, part, slots, recs, q, alpha, z, ctrl, total;
   int per_prod;                     // bytes of one producer's queue (+ alpha table)
 };
 
@@ -97,11 +120,13 @@ __host__ __device__ inline SmemV3 smem_v3(int S, bool floater, int nprod) {
   L.part = off;   off += (N_CONS == 8 ? TM * 4 * 4 : 0); // layer-3 partial sums of the upper column half
   off = (off + 15) & ~15;
   L.slots = off;  off += MAX_PROD * NSLOT * (int)sizeof(Slot);
+  off = (off + 15) & ~15;
+  L.recs = off;   off += (LRF_STEAL ? nprod * (int)sizeof(RayRec) : 0);
   L.q = off;
-  L.per_prod = QCAP * 2 + QCAP * 4 + (floater ? Sp * 4 : 0);
+  L.per_prod = QCAP * 2 + QCAP * 4 + QCAP + (floater ? Sp * 4 : 0);   // sample index, weight, slot id per entry
   L.per_prod = (L.per_prod + 15) & ~15;
   off += nprod * L.per_prod;
-  L.alpha = QCAP * 6;                                   // offset of the alpha table inside a producer block
+  L.alpha = QCAP * 7 + (16 - (QCAP * 7) % 16) % 16;     // offset of the alpha table inside a producer block
   L.z = off;      off += (Sp + 4) * 4;
   off = (off + 15) & ~15;
   L.ctrl = off;   off += (int)sizeof(Ctrl);
@@ -248,54 +273,136 @@ __device__ __noinline__ void pad_open_tile(const ProdCtx& P) {
   __syncwarp();
 }
 
-// gathers the first n (<= 32) queued samples of ray R and submits them as tile rows
-__device__ __forceinline__ void flush_rows(const ProdCtx& P, const FieldDev& F, const RaySm& R,
-                                           const float* z_s, Slot* slot, int slot_id,
-                                           const unsigned short* qk, const float* qw, int n) {
+// per-warp queue of selected samples: (sample index, weight, ray slot); entries of different rays mix
+struct WarpQ {
+  unsigned short* qk;
+  float* qw;
+  unsigned char* qs;
+  int qn;
+  unsigned long long n_app;
+};
+
+// gathers the first n (<= 32) queued samples (each with its own ray, read from its slot) and submits
+// them as tile rows.  Their slots' `pending` counts were raised when the samples were selected.
+__device__ __forceinline__ void flush_rows(const ProdCtx& P, const FieldDev& F, const float* z_s,
+                                           const Slot* slots, const WarpQ& Q, int n) {
   unsigned int start = 0;
-  if (P.lane == 0) {
-    atomicAdd(&slot->pending, n);
-    start = atomicAdd(&P.ctrl->cursor, (unsigned int)n);
-  }
+  if (P.lane == 0) start = atomicAdd(&P.ctrl->cursor, (unsigned int)n);
   start = __shfl_sync(0xffffffffu, start, 0);
   if (P.lane < n) {
     const unsigned int g = start + P.lane, T = g >> 7;
     const int row = (int)(g & (TM - 1)), b = (int)(T & 1);
-    const int k = qk[P.lane];
+    const int k = Q.qk[P.lane], sid = Q.qs[P.lane];
+    const Slot* sl = slots + sid;
+    RaySm R;
+    R.o[0] = sl->o[0]; R.o[1] = sl->o[1]; R.o[2] = sl->o[2];
+    R.vd[0] = sl->vd[0]; R.vd[1] = sl->vd[1]; R.vd[2] = sl->vd[2];
     float p[3], q[3];
     sample_pos(F, R, z_s[k], p, q);
     wait_tile_free(P.ctrl, T);
     unsigned char* a_hi = P.smem + P.L->a1 + b * (2 * OPER1_BYTES);
     app_row(F, q, a_hi, a_hi + OPER1_BYTES, row);
-    P.smem[P.L->mslot + b * TM + row] = (unsigned char)slot_id;
-    reinterpret_cast<float*>(P.smem + P.L->mw)[b * TM + row] = qw[P.lane];
+    P.smem[P.L->mslot + b * TM + row] = (unsigned char)sid;
+    reinterpret_cast<float*>(P.smem + P.L->mw)[b * TM + row] = Q.qw[P.lane];
     fence_async_smem();                  // generic-proxy writes -> visible to the tensor core
     mbar_arrive(smem_u32(&P.ctrl->full[b]));
   }
   __syncwarp();
 }
 
-// appends the lanes with on == true to the warp's queue; flushes 32 rows when it holds >= 32
-#define LRF_QUEUE_STEP(on, k, wgt)                                                             \
-  {                                                                                            \
-    const unsigned m_ = __ballot_sync(0xffffffffu, (on));                                      \
-    if (on) {                                                                                  \
-      const int pos_ = qn + __popc(m_ & ((1u << lane) - 1u));                                  \
-      qk[pos_] = (unsigned short)(k); qw[pos_] = (wgt);                                        \
-    }                                                                                          \
-    qn += __popc(m_);                                                                          \
-    __syncwarp();                                                                              \
-    if (qn >= 32) {                                                                            \
-      flush_rows(P, F, R, z_s, slot, slot_id, qk, qw, 32);                                     \
-      n_app += 32;                                                                             \
-      unsigned short tk_ = 0; float tw_ = 0.0f;                                                \
-      if (lane < qn - 32) { tk_ = qk[32 + lane]; tw_ = qw[32 + lane]; }                        \
-      __syncwarp();                                                                            \
-      if (lane < qn - 32) { qk[lane] = tk_; qw[lane] = tw_; }                                  \
-      qn -= 32;                                                                                \
-      __syncwarp();                                                                            \
-    }                                                                                          \
+// appends the lanes with on == true (mask m = their ballot) to the warp's queue; flushes 32 rows when it
+// holds >= 32.  The caller has already added popc(m) to the slot's pending count.
+__device__ __forceinline__ void queue_push(const ProdCtx& P, const FieldDev& F, const float* z_s,
+                                           const Slot* slots, WarpQ& Q, unsigned m, bool on, int k,
+                                           float wgt, int slot_id) {
+  const int lane = P.lane;
+  if (on) {
+    const int pos = Q.qn + __popc(m & ((1u << lane) - 1u));
+    Q.qk[pos] = (unsigned short)k; Q.qw[pos] = wgt; Q.qs[pos] = (unsigned char)slot_id;
   }
+  Q.qn += __popc(m);
+  Q.n_app += __popc(m);
+  __syncwarp();
+  if (Q.qn >= 32) {
+    flush_rows(P, F, z_s, slots, Q, 32);
+    unsigned short tk = 0; float tw = 0.0f; unsigned char ts = 0;
+    if (lane < Q.qn - 32) { tk = Q.qk[32 + lane]; tw = Q.qw[32 + lane]; ts = Q.qs[32 + lane]; }
+    __syncwarp();
+    if (lane < Q.qn - 32) { Q.qk[lane] = tk; Q.qw[lane] = tw; Q.qs[lane] = ts; }
+    Q.qn -= 32;
+    __syncwarp();
+  }
+}
+
+// alpha of sample k of the ray in slot-resident form (tensorBase.py:581-610); counts valid samples
+__device__ __forceinline__ float sample_alpha(const FieldDev& F, const RaySm& R, const float* z_s, int k,
+                                              int S, int& marched) {
+  const float z = z_s[k];
+  float p[3], q[3];
+  sample_pos(F, R, z, p, q);
+  bool valid = (k != S - 1);                                  // ray_valid[:, -1] = 0
+  if (valid && F.alpha_vol) valid = alpha_mask(F, p) > 0.0f;  // tensorBase.py:593-598
+  float sigma = 0.0f;
+  if (valid) {
+    sigma = feature2density(density_feature(F, q), F.density_shift, F.act);
+    ++marched;
+  }
+  const float dist = z_s[k + 1] - z;
+  float alpha = 1.0f - expf(-sigma * dist * F.distance_scale);   // tensorBase.py:610, same form
+  if (k == S - 1) alpha = 1.0f;                                  // alpha[:, -1] = 1
+  return alpha;
+}
+
+// One claimed step (32 samples) of the ray described by `rec`: see RayRec.
+__device__ __forceinline__ void process_step(const ProdCtx& P, const FieldDev& F, const BatchDev& B,
+                                             const float* z_s, Slot* slots, RayRec* rec, int s, WarpQ& Q) {
+  const int lane = P.lane, S = F.S, k = s * 32 + lane;
+  const int slot_id = *reinterpret_cast<volatile int*>(&rec->slot_id);
+  const long long ray = *reinterpret_cast<volatile long long*>(&rec->ray);
+  Slot* slot = slots + slot_id;
+  RaySm R;
+  R.o[0] = slot->o[0]; R.o[1] = slot->o[1]; R.o[2] = slot->o[2];
+  R.vd[0] = slot->vd[0]; R.vd[1] = slot->vd[1]; R.vd[2] = slot->vd[2];
+  const bool skip = (unsigned)s >= *reinterpret_cast<volatile unsigned int*>(&rec->stop_at);
+  float alpha = 0.0f;
+  int marched = 0;
+  if (!skip && k < S) alpha = sample_alpha(F, R, z_s, k, S, marched);
+  const float f = (k < S) ? (1.0f - alpha) + 1e-10f : 1.0f;
+  const float inc = warp_scan_mul(f, lane);
+  float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) exc = 1.0f;
+  const float Ploc = __shfl_sync(0xffffffffu, inc, 31);
+  if (lane == 0) {
+    *reinterpret_cast<volatile float*>(&rec->P[s]) = skip ? 0.0f : Ploc;
+    __threadfence_block();
+    atomicOr(&rec->ready, 1u << s);
+  }
+  // carry = ((1 * P[0]) * P[1]) ... * P[s-1], the sequential order
+  float carry = 1.0f;
+  if (!skip) {
+    const unsigned need = s ? (0xffffffffu >> (32 - s)) : 0u;
+    while ((*reinterpret_cast<volatile unsigned int*>(&rec->ready) & need) != need) { }
+    __threadfence_block();
+    for (int j = 0; j < s; ++j) carry *= *reinterpret_cast<volatile float*>(&rec->P[j]);
+  }
+  const bool live = !skip && !(carry < T_EPS);                  // a terminated ray's later steps contribute nothing
+  const float wgt = live ? alpha * (carry * exc) : 0.0f;
+  const float zk = (k < S) ? z_s[k] : 0.0f;
+  const float acc_s = warp_sum((live && k < S) ? wgt : 0.0f);
+  const float dep_s = warp_sum((live && k < S) ? wgt * zk : 0.0f);
+  const int marched_s = (int)warp_sum(live ? (float)marched : 0.0f);
+  if (B.weights && k < S) B.weights[(size_t)ray * S + k] = wgt;
+  if (live && carry * Ploc < T_EPS && lane == 0) atomicMin(&rec->stop_at, (unsigned)(s + 1));
+  const bool on = live && (k < S) && (wgt > F.weight_thres);    // tensorBase.py:622
+  const unsigned m = __ballot_sync(0xffffffffu, on);
+  if (lane == 0) {
+    rec->accs[s] = acc_s; rec->deps[s] = dep_s; rec->marched[s] = marched_s;
+    if (m) atomicAdd(&slot->pending, __popc(m));                // before `done`: the owner drops its token after it
+    __threadfence_block();
+    atomicOr(&rec->done, 1u << s);
+  }
+  queue_push(P, F, z_s, slots, Q, m, on, k, wgt, slot_id);
+}
 
 // =================================================================================================
 __global__ void __launch_bounds__(THREADS, 1)
@@ -317,7 +424,7 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
     mbar_init(smem_u32(&ctrl->mma1), 1);
     mbar_init(smem_u32(&ctrl->a2rdy), TM * N_CONS / 4);
     mbar_init(smem_u32(&ctrl->mma2), 1);
-    ctrl->cursor = 0; ctrl->prod_done = 0; ctrl->n_tiles_final = 0; ctrl->done = 0;
+    ctrl->cursor = 0; ctrl->prod_done = 0; ctrl->draw_done = 0; ctrl->n_tiles_final = 0; ctrl->done = 0;
     ctrl->released = 0;
     constexpr uint32_t bytes = PREP_BYTES;
     mbar_expect_tx(smem_u32(&ctrl->bar_w), bytes);
@@ -330,6 +437,8 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
   if (tid == 0) z_s[S] = F.z[S - 1];       // dist of the last sample = 0 (tensorBase.py:584-587)
   for (int e = tid; e < MAX_PROD * NSLOT * (int)sizeof(Slot) / 4; e += THREADS)
     reinterpret_cast<int*>(slots)[e] = 0;
+  if (LRF_STEAL && tid < nprod)                                      // no ray open: nothing to claim
+    reinterpret_cast<RayRec*>(smem + L.recs)[tid].next_step = 0x40000000u;
   {  // K padding 72..79 of both A1 tiles (hi and lo) is zero for the whole launch
     const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int e = tid; e < 2 * TM; e += THREADS) {
@@ -350,10 +459,18 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
     // ======================================= PRODUCER ============================================
     ProdCtx P{smem, &L, ctrl, lane};
     unsigned char* mine = smem + L.q + prod_id * L.per_prod;
-    unsigned short* qk = reinterpret_cast<unsigned short*>(mine);
-    float* qw = reinterpret_cast<float*>(mine + QCAP * 2);
+    WarpQ Q;
+    Q.qk = reinterpret_cast<unsigned short*>(mine);
+    Q.qw = reinterpret_cast<float*>(mine + QCAP * 2);
+    Q.qs = mine + QCAP * 6;
+    Q.qn = 0; Q.n_app = 0;
     float* alpha_s = reinterpret_cast<float*>(mine + L.alpha);
-    unsigned long long n_march = 0, n_app = 0;
+    RayRec* recs = reinterpret_cast<RayRec*>(smem + L.recs);
+    RayRec* rec = recs + prod_id;
+    const int n_steps = (S + 31) >> 5;
+    const bool stepwise = LRF_STEAL && !floater && n_steps <= MAXST;   // else: the owner marches its ray alone
+    const unsigned full_mask = n_steps >= 32 ? 0xffffffffu : ((1u << n_steps) - 1u);
+    unsigned long long n_march = 0;
     int next_slot = 0;
     for (;;) {
       long long ray = 0;
@@ -362,7 +479,7 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
       if (ray >= B.n_rays) break;
       RaySm R;
       setup_ray(B, ray, R);
-      // -- acquire a ray slot (pad the open tile if the consumers starve) ---------------------------
+      // -- acquire a ray slot (if the consumers starve: submit what this warp holds, pad the open tile) --
       const int slot_id = prod_id * NSLOT + next_slot;
       next_slot = (next_slot + 1 == NSLOT) ? 0 : next_slot + 1;
       Slot* slot = slots + slot_id;
@@ -371,9 +488,14 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
         if (lane == 0) st = *reinterpret_cast<volatile int*>(&slot->state);
         st = __shfl_sync(0xffffffffu, st, 0);
         if (st == 0) break;
-        if (spins == SPIN_PAD) { pad_open_tile(P); spins = 0; }
+        if (spins == SPIN_PAD) {
+          if (Q.qn > 0) { flush_rows(P, F, z_s, slots, Q, Q.qn); Q.qn = 0; }
+          pad_open_tile(P);
+          spins = 0;
+        }
       }
       if (lane == 0) {
+        slot->o[0] = R.o[0]; slot->o[1] = R.o[1]; slot->o[2] = R.o[2]; slot->nrm = R.nrm;
         slot->vd[0] = R.vd[0]; slot->vd[1] = R.vd[1]; slot->vd[2] = R.vd[2];
         slot->blend = R.blend;
         slot->rgb[0] = slot->rgb[1] = slot->rgb[2] = 0u;
@@ -383,72 +505,104 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
         *reinterpret_cast<volatile int*>(&slot->state) = 1;
       }
       __syncwarp();
-      // -- march (tensorBase.py:581-615) ------------------------------------------------------------
-      float carry = 1.0f, acc_p = 0.0f, dep_p = 0.0f, idx_p = 0.0f;
-      int qn = 0, k0 = 0, marched = 0;
-      float* wo = B.weights ? B.weights + (size_t)ray * S : nullptr;
-      for (; k0 < S; k0 += 32) {
-        const int k = k0 + lane;
-        float alpha = 0.0f;
-        if (k < S) {
-          const float z = z_s[k];
-          float p[3], q[3];
-          sample_pos(F, R, z, p, q);
-          bool valid = (k != S - 1);                                  // ray_valid[:, -1] = 0
-          if (valid && F.alpha_vol) valid = alpha_mask(F, p) > 0.0f;  // tensorBase.py:593-598
-          float sigma = 0.0f;
-          if (valid) {
-            sigma = feature2density(density_feature(F, q), F.density_shift, F.act);
-            ++marched;
-          }
-          const float dist = z_s[k + 1] - z;
-          alpha = 1.0f - expf(-sigma * dist * F.distance_scale);       // tensorBase.py:610, same form
-          if (k == S - 1) alpha = 1.0f;                               // alpha[:, -1] = 1
+      float acc = 0.0f, dep = 0.0f;
+      if (stepwise) {
+        // -- march by claimed steps (tensorBase.py:581-615); idle producers of this CTA may take steps --
+        if (lane == 0) {
+          rec->slot_id = slot_id; rec->ray = ray;
+          rec->stop_at = (unsigned)n_steps; rec->ready = 0u; rec->done = 0u;
+          __threadfence_block();
+          *reinterpret_cast<volatile unsigned int*>(&rec->next_step) = 0u;     // opens the ray for claims
         }
-        const float f = (k < S) ? (1.0f - alpha) + 1e-10f : 1.0f;
-        const float inc = warp_scan_mul(f, lane);
-        float exc = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) exc = 1.0f;
-        const float wgt = alpha * (carry * exc);
-        if (k < S) {
-          acc_p += wgt;
-          dep_p += wgt * z_s[k];
-          idx_p += wgt * (float)k;
-          if (floater) alpha_s[k] = alpha;
-          else if (wo) wo[k] = wgt;
-        }
-        carry *= __shfl_sync(0xffffffffu, inc, 31);
-        if (!floater) {
-          const bool on = (k < S) && (wgt > F.weight_thres);          // tensorBase.py:622
-          LRF_QUEUE_STEP(on, k, wgt)
-          if (carry < T_EPS) { k0 += 32; break; }                      // early ray termination
-        }
-      }
-      if (!floater && wo)
-        for (int k = k0 + lane; k < S; k += 32) wo[k] = 0.0f;          // terminated tail
-      const float acc = warp_sum(acc_p), dep = warp_sum(dep_p);
-      if (floater) {                                                   // tensorBase.py:617-620
-        const float lim = warp_sum(idx_p) * B.floater_thresh;
         __syncwarp();
-        float c2 = 1.0f;
-        for (int kb = 0; kb < S; kb += 32) {
-          const int k = kb + lane;
-          float a = (k < S) ? alpha_s[k] : 0.0f;
-          if ((float)k < lim) a = 0.0f;
-          if (k == S - 1) a = 1.0f;
-          const float f = (k < S) ? (1.0f - a) + 1e-10f : 1.0f;
+        for (;;) {
+          unsigned int st = 0;
+          if (lane == 0) st = atomicAdd(&rec->next_step, 1u);
+          st = __shfl_sync(0xffffffffu, st, 0);
+          if (st >= (unsigned)n_steps) break;
+          if (st >= *reinterpret_cast<volatile unsigned int*>(&rec->stop_at)) {
+            // the ray has terminated (T < 1e-10): close it -- this step and every unclaimed one contribute
+            // nothing (steps a helper has already claimed past this point skip themselves)
+            unsigned int rem = 0;
+            if (lane == 0) rem = atomicExch(&rec->next_step, 0x40000000u);
+            rem = min(__shfl_sync(0xffffffffu, rem, 0), (unsigned)n_steps);
+            unsigned int mask = 1u << st;
+            for (unsigned int j = rem; j < (unsigned)n_steps; ++j) mask |= 1u << j;
+            if (lane < n_steps && ((mask >> lane) & 1u)) {
+              rec->accs[lane] = 0.0f; rec->deps[lane] = 0.0f; rec->marched[lane] = 0;
+              *reinterpret_cast<volatile float*>(&rec->P[lane]) = 0.0f;
+            }
+            if (B.weights)
+              for (int k = (int)st * 32 + lane; k < S; k += 32)
+                if ((mask >> (k >> 5)) & 1u) B.weights[(size_t)ray * S + k] = 0.0f;
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); atomicOr(&rec->ready, mask); atomicOr(&rec->done, mask); }
+            break;
+          }
+          process_step(P, F, B, z_s, slots, rec, (int)st, Q);
+        }
+        while (*reinterpret_cast<volatile unsigned int*>(&rec->done) != full_mask) { }   // helpers' steps
+        __threadfence_block();
+        int marched = 0;
+        for (int j = 0; j < n_steps; ++j) { acc += rec->accs[j]; dep += rec->deps[j]; marched += rec->marched[j]; }
+        n_march += (unsigned long long)marched;
+      } else {
+        // -- sequential march of the whole ray by its owner (floater filter, very long sample tables) ----
+        float carry = 1.0f, acc_p = 0.0f, dep_p = 0.0f, idx_p = 0.0f;
+        int k0 = 0, marched = 0;
+        float* wo = B.weights ? B.weights + (size_t)ray * S : nullptr;
+        for (; k0 < S; k0 += 32) {
+          const int k = k0 + lane;
+          float alpha = 0.0f;
+          if (k < S) alpha = sample_alpha(F, R, z_s, k, S, marched);
+          const float f = (k < S) ? (1.0f - alpha) + 1e-10f : 1.0f;
           const float inc = warp_scan_mul(f, lane);
           float exc = __shfl_up_sync(0xffffffffu, inc, 1);
           if (lane == 0) exc = 1.0f;
-          const float wgt = a * (c2 * exc);
-          c2 *= __shfl_sync(0xffffffffu, inc, 31);
-          if (k < S && wo) wo[k] = wgt;
-          const bool on = (k < S) && (wgt > F.weight_thres);
-          LRF_QUEUE_STEP(on, k, wgt)
+          const float wgt = alpha * (carry * exc);
+          if (k < S) {
+            acc_p += wgt;
+            dep_p += wgt * z_s[k];
+            idx_p += wgt * (float)k;
+            if (floater) alpha_s[k] = alpha;
+            else if (wo) wo[k] = wgt;
+          }
+          carry *= __shfl_sync(0xffffffffu, inc, 31);
+          if (!floater) {
+            const bool on = (k < S) && (wgt > F.weight_thres);          // tensorBase.py:622
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (lane == 0 && m) atomicAdd(&slot->pending, __popc(m));
+            queue_push(P, F, z_s, slots, Q, m, on, k, wgt, slot_id);
+            if (carry < T_EPS) { k0 += 32; break; }                      // early ray termination
+          }
         }
+        if (!floater && wo)
+          for (int k = k0 + lane; k < S; k += 32) wo[k] = 0.0f;          // terminated tail
+        acc = warp_sum(acc_p); dep = warp_sum(dep_p);
+        if (floater) {                                                   // tensorBase.py:617-620
+          const float lim = warp_sum(idx_p) * B.floater_thresh;
+          __syncwarp();
+          float c2 = 1.0f;
+          for (int kb = 0; kb < S; kb += 32) {
+            const int k = kb + lane;
+            float a = (k < S) ? alpha_s[k] : 0.0f;
+            if ((float)k < lim) a = 0.0f;
+            if (k == S - 1) a = 1.0f;
+            const float f = (k < S) ? (1.0f - a) + 1e-10f : 1.0f;
+            const float inc = warp_scan_mul(f, lane);
+            float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane == 0) exc = 1.0f;
+            const float wgt = a * (c2 * exc);
+            c2 *= __shfl_sync(0xffffffffu, inc, 31);
+            if (k < S && wo) wo[k] = wgt;
+            const bool on = (k < S) && (wgt > F.weight_thres);
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (lane == 0 && m) atomicAdd(&slot->pending, __popc(m));
+            queue_push(P, F, z_s, slots, Q, m, on, k, wgt, slot_id);
+          }
+        }
+        n_march += (unsigned long long)warp_sum((float)marched);
       }
-      if (qn > 0) { flush_rows(P, F, R, z_s, slot, slot_id, qk, qw, qn); n_app += qn; }
-      n_march += (unsigned long long)warp_sum((float)marched);
       // -- depth now, colour when the last row of this ray has been composited ---------------------
       if (lane == 0) {
         float dpt = __fdiv_rn(dep, R.nrm) * R.blend;                   // tensorBase.py:615
@@ -462,8 +616,33 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
       }
       __syncwarp();
     }
-    // -- no more rays: the last producer completes the open tile and publishes the tile count ------
-    if (lane == 0 && B.stats) { atomicAdd(B.stats, n_march); atomicAdd(B.stats + 1, n_app); }
+    // -- the global ray queue is empty: help the rays still in flight in this CTA, step by step ------
+    if (lane == 0) { __threadfence_block(); atomicAdd(&ctrl->draw_done, 1u); }
+    if (stepwise) {
+      for (;;) {
+        bool any = false;
+        for (int r = 1; r < nprod; ++r) {
+          RayRec* other = recs + ((prod_id + r) % nprod);
+          for (;;) {
+            if (*reinterpret_cast<volatile unsigned int*>(&other->next_step) >= (unsigned)n_steps) break;
+            unsigned int st = 0;
+            if (lane == 0) st = atomicAdd(&other->next_step, 1u);
+            st = __shfl_sync(0xffffffffu, st, 0);
+            if (st >= (unsigned)n_steps) break;
+            __threadfence_block();
+            process_step(P, F, B, z_s, slots, other, (int)st, Q);
+            any = true;
+          }
+        }
+        if (!any) {
+          if (*reinterpret_cast<volatile unsigned int*>(&ctrl->draw_done) >= (unsigned)nprod) break;
+          __nanosleep(200);
+        }
+      }
+    }
+    if (Q.qn > 0) { flush_rows(P, F, z_s, slots, Q, Q.qn); Q.qn = 0; }
+    // -- the last producer completes the open tile and publishes the tile count ----------------------
+    if (lane == 0 && B.stats) { atomicAdd(B.stats, n_march); atomicAdd(B.stats + 1, Q.n_app); }
     unsigned int d = 0;
     if (lane == 0) { __threadfence_block(); d = atomicAdd(&ctrl->prod_done, 1u); }
     d = __shfl_sync(0xffffffffu, d, 0);
