@@ -123,6 +123,15 @@ typedef struct LrfOutputs {
   int32_t n_peers;            /* 0 = no exchange; <= LRF_MAX_PEERS */
   float *peer_pix[16];
   float *mc_pix;
+  /* In-kernel step signalling (optional, signal_seq > 0): peer_flags[p] = peer p's [n_peers] uint64 flag
+   * array (peer-mapped; peer_flags[rank] is this GPU's own).  Before its first peer store the launch waits
+   * until all local flags have reached wait_seq (the peers are done with the buffer about to be overwritten;
+   * 0 = no wait); the LAST CTA to finish release-stores signal_seq into slot `rank` of every peer's array,
+   * after all pixel stores of the launch.  With wait_seq = signal_seq - lag (lag >= 1) this replaces
+   * lrf_peer_signal_wait altogether: a step costs no extra launch. */
+  unsigned long long *peer_flags[16];
+  int32_t rank;
+  unsigned long long signal_seq, wait_seq;
 } LrfOutputs;
 #define LRF_MAX_PEERS 16
 

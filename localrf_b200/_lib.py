@@ -62,7 +62,8 @@ class LrfBatch(C.Structure):
 class LrfOutputs(C.Structure):
     _fields_ = [("rgb", _vp), ("depth", _vp), ("weights", _vp), ("directions", _vp),
                 ("ij", _vp), ("pix", _vp), ("stats", _vp),
-                ("n_peers", C.c_int32), ("peer_pix", _vp * 16), ("mc_pix", _vp)]
+                ("n_peers", C.c_int32), ("peer_pix", _vp * 16), ("mc_pix", _vp),
+                ("peer_flags", _vp * 16), ("rank", C.c_int32), ("signal_seq", C.c_uint64), ("wait_seq", C.c_uint64)]
 
 
 class LrfGradients(C.Structure):

@@ -95,7 +95,7 @@ int device_info(DevInfo& d) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
     cache[dev].n_sms = p.multiProcessorCount;
     cache[dev].max_smem = (int)p.sharedMemPerBlockOptin;
-    e = cudaMalloc(&cache[dev].sched, SCHED_RING * sizeof(unsigned long long));
+    e = cudaMalloc(&cache[dev].sched, 2 * SCHED_RING * sizeof(unsigned long long));
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(ray counters)");
     cache[dev].ok = true;
   }
@@ -202,7 +202,17 @@ int lrf_render(const LrfField* f, const void* prepared, const LrfBatch* b, const
   int rc = make_field(f, true, true, prepared, F);
   if (rc != LRF_OK) return rc;
   if (b->n_rays < 0) return fail(LRF_ERR_INVALID, "n_rays < 0");
-  if (b->n_rays == 0) return LRF_OK;
+  if (b->n_rays == 0) {
+    // nothing to render; a rank with an empty shard must still publish its step to the peers
+    if (o->signal_seq && o->n_peers >= 1 && o->rank >= 0 && o->rank < o->n_peers) {
+      for (int p = 0; p < o->n_peers; ++p)
+        if (!o->peer_flags[p]) return fail(LRF_ERR_INVALID, "peer_flags pointer is NULL");
+      cudaError_t e = lrf::launch_peer_barrier(o->peer_flags, o->rank, o->n_peers, o->signal_seq, 0ull,
+                                               (cudaStream_t)stream);
+      if (e != cudaSuccess) return cuda_fail(e, "peer_barrier_kernel");
+    }
+    return LRF_OK;
+  }
   if (!o->pix && (!o->rgb || !o->depth)) return fail(LRF_ERR_INVALID, "rgb/depth output is NULL");
   lrf::BatchDev B;
   memset(&B, 0, sizeof(B));
@@ -257,13 +267,25 @@ int lrf_render(const LrfField* f, const void* prepared, const LrfBatch* b, const
       }
     }
   }
+  B.signal_seq = 0; B.wait_seq = 0; B.rank = 0;
+  if (o->signal_seq) {
+    if (o->n_peers < 1 || o->rank < 0 || o->rank >= o->n_peers || o->wait_seq > o->signal_seq)
+      return fail(LRF_ERR_INVALID, "in-kernel signalling needs n_peers >= 1, 0 <= rank < n_peers, wait_seq <= signal_seq");
+    for (int p = 0; p < o->n_peers; ++p) {
+      if (!o->peer_flags[p] || ((uintptr_t)o->peer_flags[p] & 7))
+        return fail(LRF_ERR_INVALID, "peer_flags pointers must be non-NULL and 8-byte aligned");
+      B.peer_flags[p] = o->peer_flags[p];
+    }
+    B.signal_seq = o->signal_seq; B.wait_seq = o->wait_seq; B.rank = o->rank;
+  }
   DevInfo d;
   rc = device_info(d);
   if (rc != LRF_OK) return rc;
   const size_t smem = lrf::render_smem_bytes(F.S, B.floater_thresh > 0.0f, d.max_smem);
   if ((long long)smem > d.max_smem)
     return fail(LRF_ERR_UNSUPPORTED, "sample table too long for the shared-memory budget");
-  B.sched = d.sched + d.next;
+  B.sched = d.sched + 2 * d.next;                                   // [ray counter, finished-CTA counter]
+  B.done_ctr = reinterpret_cast<unsigned int*>(d.sched + 2 * d.next + 1);
   cudaError_t e = lrf::launch_render(F, B, d.n_sms, d.max_smem, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "render_kernel");
   return LRF_OK;

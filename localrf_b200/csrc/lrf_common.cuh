@@ -86,6 +86,10 @@ struct BatchDev {
   int n_peers;                 // fused pixel exchange: peers that receive this rank's pixels
   float* peer_pix[16];
   float* mc_pix;               // NVLS multicast address (one multimem store reaches every peer)
+  unsigned long long* peer_flags[16];   // in-kernel step signalling (signal_seq > 0)
+  int rank;
+  unsigned long long signal_seq, wait_seq;
+  unsigned int* done_ctr;      // CTAs of this launch that have finished (library-owned, zeroed per launch)
 };
 
 // ---- sampling helpers -------------------------------------------------------------------------

@@ -447,6 +447,14 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
     }
   }
   if (warp == W_CONS) tmem_alloc(smem_u32(&ctrl->tmem), TMEM_COLS);
+  if (B.signal_seq && B.wait_seq && tid < B.n_peers) {
+    // fused pixel exchange: the peers must be done with the gathered buffer this launch overwrites
+    const unsigned long long* local = B.peer_flags[B.rank] + tid;
+    unsigned long long v = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(local) : "memory");
+    } while (v < B.wait_seq);
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -796,6 +804,19 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
   }
   __syncthreads();
   if (warp == W_CONS) tmem_dealloc(tmem, TMEM_COLS);
+  if (B.signal_seq && tid == 0) {
+    // every pixel store of this CTA is ordered before the barrier above; the last CTA of the launch
+    // publishes the step to all peers (release at system scope, after a cumulative fence)
+    __threadfence_system();
+    const unsigned int old = atomicAdd(B.done_ctr, 1u);
+    if (old == gridDim.x - 1) {
+      __threadfence_system();
+      for (int p = 0; p < B.n_peers; ++p) {
+        unsigned long long* remote = B.peer_flags[p] + B.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(B.signal_seq) : "memory");
+      }
+    }
+  }
 }
 
 // ---- host-side launcher --------------------------------------------------------------------------
@@ -832,7 +853,7 @@ cudaError_t launch_render(const FieldDev& F, const BatchDev& B, int n_sms, int m
     if (e != cudaSuccess) return e;
     configured[dev] = smem;
   }
-  e = cudaMemsetAsync(B.sched, 0, sizeof(unsigned long long), stream);
+  e = cudaMemsetAsync(B.sched, 0, 2 * sizeof(unsigned long long), stream);   // ray counter + finished-CTA counter
   if (e != cudaSuccess) return e;
   // a CTA per SM, but never more CTAs than there are groups of 8 rays
   long long want = (B.n_rays + 7) / 8;

@@ -117,14 +117,29 @@ class PixelExchange:
         o.n_peers = self.world
         for p in range(self.world):
             o.peer_pix[p] = self.ptrs[p] + off
+            o.peer_flags[p] = self.ptrs[p] + self.n_buf * self.buf_bytes
         o.mc_pix = (self.mc_ptr + off) if self.mc_ptr else None
+        # the kernel itself publishes the step (its last CTA release-stores the flags after all pixel
+        # stores) and, when the consumer lags, first waits for the peers to be done with this buffer
+        o.rank = self.rank
+        o.signal_seq = self.seq + 1
+        o.wait_seq = max(self.seq + 1 - self.lag, 0) if self.lag >= 1 else 0
 
     def close_step(self, stream):
-        """Enqueues signal(step) + wait(step - lag); afterwards `gathered(n)` holds every rank's pixels of
-        step (this - lag)."""
+        """Closes the step the render kernel has just signalled.  lag 0: enqueues the wait for every peer's
+        flag of THIS step (one small kernel); lag >= 1: nothing to enqueue -- the next step's render kernel
+        waits for step (next - lag) before its first store.  `gathered(n)` then refers to step (this - lag),
+        complete once the following render launch (lag >= 1) or this wait (lag 0) has run."""
+        self.seq += 1
+        if self.lag == 0:
+            self._lib.check(self._lib.lib().lrf_peer_signal_wait(self._flag_ptrs, self.rank, self.world, self.seq,
+                                                                 self.seq, stream))
+
+    def skip_step(self, stream):
+        """A rank whose shard of this step is empty renders nothing but still publishes the step."""
         self.seq += 1
         self._lib.check(self._lib.lib().lrf_peer_signal_wait(self._flag_ptrs, self.rank, self.world, self.seq,
-                                                             max(self.seq - self.lag, 0), stream))
+                                                             self.seq if self.lag == 0 else 0, stream))
 
     def gathered(self, n_rays):
         off = (max(self.seq - self.lag, 0) % self.n_buf) * self.buf_bytes
@@ -145,7 +160,10 @@ def render_sharded(local_tensorfs, ray_ids, view_ids, W, H, group=None, exchange
         return gather_pixels(rgb, depth, n, group)
     if n > exchange.max_rays:
         raise ValueError(f"batch of {n} rays exceeds the exchange buffer ({exchange.max_rays})")
-    local_tensorfs(ray_ids[lo:hi], view_ids, W, H, exchange=(exchange, lo), **kw)
+    if hi > lo:
+        local_tensorfs(ray_ids[lo:hi], view_ids, W, H, exchange=(exchange, lo), **kw)
+    else:
+        exchange.skip_step(C.c_void_p(torch.cuda.current_stream(exchange.device).cuda_stream))
     full = exchange.gathered(n)
     return full[:, :3], full[:, 3]
 

@@ -29,13 +29,24 @@ def _worker(rank, world, port, q):
         ok_x, ok_n = True, True
         with torch.no_grad():
             for step, (lo, n) in enumerate([(0, 4096), (123456, 4096), (5000, 1001), (640000 - 17, 17),
-                                            (300000, 20000)]):
+                                            (300000, 20000), (1000, 5)]):
                 ids = torch.arange(lo, lo + n, dtype=torch.int64, device=dev)
                 rgb, depth, _, _ = lt(ids, view, 800, 800, is_train=False)
                 r1, d1 = render_sharded(lt, ids, view, 800, 800, exchange=xch, is_train=False)
                 ok_x &= bool(torch.equal(r1, rgb) and torch.equal(d1, depth))
                 r2, d2 = render_sharded(lt, ids, view, 800, 800, is_train=False)
                 ok_n &= bool(torch.equal(r2, rgb) and torch.equal(d2, depth))
+        # consumer lag 1 (no barrier kernel at all: the render kernel waits / signals): step i returns step i-1
+        xl = PixelExchange(8192, device=dev, lag=1)
+        prev = None
+        with torch.no_grad():
+            for lo in (0, 4096, 77 * 4096, 100 * 4096, 8192):
+                ids = torch.arange(lo, lo + 4096, dtype=torch.int64, device=dev)
+                rgb, depth, _, _ = lt(ids, view, 800, 800, is_train=False)
+                r1, d1 = render_sharded(lt, ids, view, 800, 800, exchange=xl, is_train=False)
+                if prev is not None:
+                    ok_x &= bool(torch.equal(r1, prev[0]) and torch.equal(d1, prev[1]))
+                prev = (rgb, depth)
         # unicast P2P stores as well when the multicast path was taken above
         if xch.mc_ptr:
             xu = PixelExchange(8192, device=dev, use_multicast=False)
