@@ -73,7 +73,7 @@ struct Slot {                       // one ray in flight between a producer and 
 };
 
 #ifndef LRF_STEAL
-#define LRF_STEAL 1                 // idle producers help the in-flight rays of their CTA, one 32-sample step at a time
+#define LRF_STEAL 0                 // (measured: correct but 10 % slower) idle producers help the in-flight rays of their CTA, one 32-sample step at a time
 #endif
 constexpr int MAXST = 32;           // steps a ray may have for step stealing (S <= 1024); longer rays march sequentially
 
