@@ -38,8 +38,10 @@ N > 1 (torchrun, one rank per GPU), field replicated, rays sharded, no data-path
   --scaling frame   the 640 000 rays of a frame are split N ways, one exchange per frame
   The rendered [rays,4] pixels (rgb+depth) are exchanged by the render kernel itself: the thread that
   finishes a ray stores it into every peer's gathered buffer (symmetric memory over NVLink/NVSwitch,
-  NVLS multicast when available) and a one-CTA flag barrier closes the step (--exchange fused);
-  --exchange nccl uses one ncclAllGather per step instead.
+  NVLS multicast when available); the kernel's last CTA publishes the step in every peer's flag array and
+  the next launches wait (in their prologue) for the peers' step s-1-lag -- no barrier launch, no collective
+  (--exchange fused, --lag 1 default; --lag 0 = same-step barrier kernel); --exchange nccl uses one
+  ncclAllGather per step instead.
 """
 import argparse
 import json
@@ -457,8 +459,9 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "distB", "incoherent", "cfg3", "cfg5"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong", "frame"])
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
-    ap.add_argument("--lag", type=int, default=1, help="fused exchange: steps the consumer of the gathered "
-                    "pixels runs behind (1 = double-buffered, 0 = same-step barrier)")
+    ap.add_argument("--lag", type=int, default=1, help="fused exchange: steps of slack between a rank and its "
+                    "slowest peer (0 = same-step barrier; L >= 1: step s waits for the peers' step s-1-L, the "
+                    "gathered image of step s-1-L is complete after the launch of step s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--grid", type=int, default=None)
@@ -510,7 +513,8 @@ def main():
             try:
                 xch = PixelExchange(rays_per_step_global, device=dev, lag=args.lag)
                 exchange_kind = ("fused (multimem stores)" if xch.mc_ptr else "fused (peer stores)") + \
-                    f", consumer lag {args.lag} step(s)"
+                    (f", slack {args.lag} step(s): no barrier launch, step s waits for the peers' step s-{1 + args.lag}"
+                     if args.lag >= 1 else ", same-step barrier kernel")
             except Exception as e:
                 print(f"bench: symmetric memory unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
                 exchange_kind = "nccl (fused unavailable)"

@@ -68,14 +68,17 @@ def gather_pixels(rgb, depth, n_total, group=None):
 class PixelExchange:
     """Gathered pixel buffer in symmetric memory + the step barrier (fused pixel exchange).
 
-    `lag` = how many steps the consumer runs behind the producers.  lag 0 (render_sharded): closing step i
-    waits until every peer has pushed step i.  lag 1 (a renderer's steady state): closing step i pushes
-    the flag of step i and waits for step i-1 only, which the peers finished a whole step ago -- no rank
-    ever waits for the slowest peer of the same step; `gathered()` then returns step i-1.
-    2 (lag + 1) buffers of [max_rays, 4] rotate.  Why that many: a rank stores step s into the buffer
-    step s - 2(lag+1) used; before launching step s it has waited (closing step s-1) for every peer's
-    signal of step s-1-lag, and a peer issues that signal only after -- in its stream order -- it has
-    consumed the gathered pixels of step s-2-2lag, the previous occupant of the buffer.
+    `lag` = steps of slack between a rank and its slowest peer.
+    lag 0 (render_sharded): the kernel publishes step i, a small wait kernel closes it when every peer has
+    published step i -- every rank returns the complete image of the same step; 2 buffers alternate.
+    lag L >= 1 (a renderer's steady state, no extra launch at all): the render kernel of step s first waits
+    until every peer has published step s-1-L (so a rank never stalls on a peer that is less than L steps
+    behind: with different batches per rank the step time is the MEAN over the ranks' batches, not the
+    per-step maximum), then stores its pixels, and its last CTA publishes step s.  After the launch of
+    step s, `gathered()` is the complete image of step s-1-L.  2L+4 buffers rotate.  Safety: step s is
+    stored into the buffer step u = s-2L-4 used; a peer reads step u between its launches u+1+L and u+2+L
+    and publishes flag u+2+L after that read (stream order); before launching step s this rank has seen
+    every peer's flag s-1-L >= u+2+L  (needs 2L+3 buffers; one more keeps the count even).
     """
     FLAG_BYTES = 16 * 8
 
@@ -90,7 +93,7 @@ class PixelExchange:
         self.max_rays = int(max_rays)
         self.buf_bytes = (self.max_rays * 16 + 255) // 256 * 256
         self.lag = int(lag)
-        self.n_buf = 2 * (self.lag + 1)
+        self.n_buf = 2 if self.lag == 0 else 2 * self.lag + 4
         total = self.n_buf * self.buf_bytes + self.FLAG_BYTES
         self.mem = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
         self.mem.zero_()
@@ -123,13 +126,12 @@ class PixelExchange:
         # stores) and, when the consumer lags, first waits for the peers to be done with this buffer
         o.rank = self.rank
         o.signal_seq = self.seq + 1
-        o.wait_seq = max(self.seq + 1 - self.lag, 0) if self.lag >= 1 else 0
+        o.wait_seq = max(self.seq - self.lag, 0) if self.lag >= 1 else 0
 
     def close_step(self, stream):
-        """Closes the step the render kernel has just signalled.  lag 0: enqueues the wait for every peer's
-        flag of THIS step (one small kernel); lag >= 1: nothing to enqueue -- the next step's render kernel
-        waits for step (next - lag) before its first store.  `gathered(n)` then refers to step (this - lag),
-        complete once the following render launch (lag >= 1) or this wait (lag 0) has run."""
+        """Closes the step the render kernel has just published.  lag 0: enqueues the wait for every peer's
+        flag of THIS step (one small kernel); lag >= 1: nothing to enqueue.  `gathered(n)` then refers to
+        step (this - 0) resp. (this - 1 - lag), which is complete at that point of the stream."""
         self.seq += 1
         if self.lag == 0:
             self._lib.check(self._lib.lib().lrf_peer_signal_wait(self._flag_ptrs, self.rank, self.world, self.seq,
@@ -141,8 +143,12 @@ class PixelExchange:
         self._lib.check(self._lib.lib().lrf_peer_signal_wait(self._flag_ptrs, self.rank, self.world, self.seq,
                                                              self.seq if self.lag == 0 else 0, stream))
 
+    def gathered_step(self):
+        """The step whose complete image `gathered()` returns now."""
+        return self.seq if self.lag == 0 else max(self.seq - 1 - self.lag, 0)
+
     def gathered(self, n_rays):
-        off = (max(self.seq - self.lag, 0) % self.n_buf) * self.buf_bytes
+        off = (self.gathered_step() % self.n_buf) * self.buf_bytes
         return self.mem[off:off + n_rays * 16].view(torch.float32).view(n_rays, 4)
 
 

@@ -36,17 +36,17 @@ def _worker(rank, world, port, q):
                 ok_x &= bool(torch.equal(r1, rgb) and torch.equal(d1, depth))
                 r2, d2 = render_sharded(lt, ids, view, 800, 800, is_train=False)
                 ok_n &= bool(torch.equal(r2, rgb) and torch.equal(d2, depth))
-        # consumer lag 1 (no barrier kernel at all: the render kernel waits / signals): step i returns step i-1
+        # lag 1 (no barrier kernel at all: the render kernel waits / publishes): step i returns step i-2
         xl = PixelExchange(8192, device=dev, lag=1)
-        prev = None
+        hist = []
         with torch.no_grad():
-            for lo in (0, 4096, 77 * 4096, 100 * 4096, 8192):
+            for lo in (0, 4096, 77 * 4096, 100 * 4096, 8192, 50 * 4096, 3 * 4096):
                 ids = torch.arange(lo, lo + 4096, dtype=torch.int64, device=dev)
                 rgb, depth, _, _ = lt(ids, view, 800, 800, is_train=False)
                 r1, d1 = render_sharded(lt, ids, view, 800, 800, exchange=xl, is_train=False)
-                if prev is not None:
-                    ok_x &= bool(torch.equal(r1, prev[0]) and torch.equal(d1, prev[1]))
-                prev = (rgb, depth)
+                hist.append((rgb, depth))
+                if len(hist) >= 3:
+                    ok_x &= bool(torch.equal(r1, hist[-3][0]) and torch.equal(d1, hist[-3][1]))
         # unicast P2P stores as well when the multicast path was taken above
         if xch.mc_ptr:
             xu = PixelExchange(8192, device=dev, use_multicast=False)
