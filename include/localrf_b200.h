@@ -28,7 +28,8 @@
  * This is exactly the memory of the reference's [1,C,H,W] / [1,C,L,1] parameters when they are
  * allocated with torch.channels_last; lrf_repack_nchw_to_nhwc() converts a contiguous NCHW tensor.
  * C = 8 (density) and 24 (appearance) per plane are the reference defaults (opt.py:117-119) and
- * the only component counts built so far; app_dim = 27, featureC = 128, positional encodings 0.
+ * the only component counts built so far; app_dim = 27, featureC = 128; positional encodings
+ * fea_pe / view_pe 0..8 (0, 0 is the reference default and the fastest path; lrf_render only).
  */
 #ifndef LOCALRF_B200_H
 #define LOCALRF_B200_H
@@ -61,10 +62,10 @@ typedef struct LrfField {
   int32_t app_dim;            /* 27 */
   const float *basis;         /* basis_mat.weight [app_dim][3*n_acomp]  tensoRF.py:25-27 */
   int32_t featureC;           /* 128 */
-  int32_t fea_pe, view_pe;    /* 0, 0 */
-  const float *w1, *b1;       /* renderModule.mlp[0]      [featureC][app_dim], [featureC] */
+  int32_t fea_pe, view_pe;    /* positional encodings of the MLP inputs (tensorBase.py:14-21,115-125); 0..8 */
+  const float *w1, *b1;       /* renderModule.mlp[0]      [featureC][app_dim (1 + 2 fea_pe)], [featureC] */
   const float *w2, *b2;       /* renderModule.mlp[2]      [featureC][featureC], [featureC] */
-  const float *w3, *b3;       /* renderModule.mlp_view[0] [3][featureC+3], [3] */
+  const float *w3, *b3;       /* renderModule.mlp_view[0] [3][featureC + 3 (1 + 2 view_pe)], [3] */
   const float *alpha_vol;     /* AlphaGridMask.alpha_volume [D][H][W], or NULL  tensorBase.py:38-62 */
   int32_t alpha_dims[3];      /* D, H, W */
   float alpha_aabb[6];
@@ -100,6 +101,9 @@ typedef struct LrfBatch {
   int32_t finalize;           /* 1: apply exposure (if any) and clamp(0,1) to rgb   (:481-497) */
   int32_t white_bg;           /* tensorBase.py:633-634 (the caller resolves the train-mode coin) */
   float floater_thresh;       /* tensorBase.py:617-620 */
+  int32_t refine;             /* MLPRender_Fea_late_view's `refine` (tensorBase.py:118-124; LocalTensorfs passes
+                                 is_refining, local_tensorfs.py:463): 0 = zeros instead of the feature encoding.
+                                 Only read when fea_pe > 0. */
 } LrfBatch;
 
 typedef struct LrfOutputs {
@@ -142,8 +146,11 @@ const char *lrf_last_error(void);
  * time, so a stale library or a drifted mirror fails loudly instead of mis-reading arguments. */
 size_t lrf_sizeof(int32_t which);
 
-/* Device bytes of the per-field "prepared" block (folded / re-laid-out MLP weights). */
+/* Device bytes of the per-field "prepared" block (folded / re-laid-out MLP weights) of a field without
+ * positional encodings; lrf_prepared_bytes_for() covers every field (fea_pe / view_pe in [0, 8]; 0 if not
+ * built).  A field with encodings needs the block 1024-byte aligned (its layer-1 operand is streamed by TMA). */
 size_t lrf_prepared_bytes(void);
+size_t lrf_prepared_bytes_for(const LrfField *field);
 /* Builds the prepared block from the field's current MLP / basis weights.  Call again whenever
  * those parameters change (every optimiser step while training). */
 int lrf_field_prepare(const LrfField *field, void *prepared, lrf_stream_t stream);

@@ -55,7 +55,7 @@ class LrfBatch(C.Structure):
         ("blend_stride", C.c_int64),
         ("exposure", _vp),
         ("accumulate", C.c_int32), ("finalize", C.c_int32), ("white_bg", C.c_int32),
-        ("floater_thresh", C.c_float),
+        ("floater_thresh", C.c_float), ("refine", C.c_int32),
     ]
 
 
@@ -72,7 +72,7 @@ class LrfGradients(C.Structure):
                 ("d_w3", _vp), ("d_b3", _vp)]
 
 
-EXPORTS = ["lrf_version", "lrf_sizeof", "lrf_last_error", "lrf_prepared_bytes", "lrf_field_prepare",
+EXPORTS = ["lrf_version", "lrf_sizeof", "lrf_last_error", "lrf_prepared_bytes", "lrf_prepared_bytes_for", "lrf_field_prepare",
            "lrf_render", "lrf_mlp_forward", "lrf_app_products", "lrf_density_feature_backward",
            "lrf_app_products_backward", "lrf_density_feature", "lrf_app_feature", "lrf_repack_nchw_to_nhwc",
            "lrf_launch_info", "lrf_prepared_backward_bytes", "lrf_backward_scratch_bytes",
@@ -138,6 +138,8 @@ def lib():
     L.lrf_version.restype = C.c_int
     L.lrf_last_error.restype = C.c_char_p
     L.lrf_prepared_bytes.restype = C.c_size_t
+    L.lrf_prepared_bytes_for.restype = C.c_size_t
+    L.lrf_prepared_bytes_for.argtypes = [C.POINTER(LrfField)]
     L.lrf_field_prepare.argtypes = [C.POINTER(LrfField), _vp, _vp]
     L.lrf_render.argtypes = [C.POINTER(LrfField), _vp, C.POINTER(LrfBatch), C.POINTER(LrfOutputs), _vp]
     L.lrf_mlp_forward.argtypes = [_vp, _vp, _vp, C.c_int64, _vp, _vp]

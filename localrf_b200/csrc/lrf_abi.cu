@@ -8,13 +8,16 @@
 #include "lrf_common.cuh"
 
 namespace lrf {
-size_t render_smem_bytes(int S, bool floater, int max_smem);
+size_t render_smem_bytes(int S, bool floater, int max_smem, bool pe);
 int render_threads();
 cudaError_t launch_render(const FieldDev& F, const BatchDev& B, int n_sms, int max_smem,
                           cudaStream_t stream);
 cudaError_t launch_prepare(const float* basis, const float* w1, const float* b1, const float* w2,
                            const float* b2, const float* w3, const float* b3, unsigned char* prep,
                            cudaStream_t stream);
+cudaError_t launch_prepare_pe(const float* basis, const float* w1, const float* b1, const float* w2,
+                              const float* b2, const float* w3, const float* b3, int fea_pe, int view_pe,
+                              unsigned char* prep, cudaStream_t stream);
 cudaError_t launch_mlp(const float* prep, const float* feats, const float* viewdirs, long long M,
                        float* rgb, int n_sms, cudaStream_t stream);
 cudaError_t launch_density_feature(const FieldDev& F, const float* xyz, long long M, float* out,
@@ -106,7 +109,7 @@ int device_info(DevInfo& d) {
 
 // validates the parts of a field every entry point needs and fills the device-side view
 int make_field(const LrfField* f, bool need_mlp, bool need_table, const void* prepared,
-               lrf::FieldDev& F) {
+               lrf::FieldDev& F, bool allow_pe = false) {
   if (!f) return fail(LRF_ERR_INVALID, "field is NULL");
   if (f->n_dcomp != lrf::CD || f->n_acomp != lrf::CA)
     return fail(LRF_ERR_UNSUPPORTED, "only density_n_comp=8 / appearance_n_comp=24 per plane are built");
@@ -146,9 +149,15 @@ int make_field(const LrfField* f, bool need_mlp, bool need_table, const void* pr
   if (need_mlp) {
     if (f->app_dim != lrf::APP_DIM || f->featureC != lrf::FC)
       return fail(LRF_ERR_UNSUPPORTED, "only app_dim=27 / featureC=128 are built");
-    if (f->fea_pe != 0 || f->view_pe != 0)
-      return fail(LRF_ERR_UNSUPPORTED, "positional encodings (fea_pe/view_pe > 0) are not built yet");
+    if (f->fea_pe < 0 || f->view_pe < 0) return fail(LRF_ERR_INVALID, "fea_pe / view_pe must be >= 0");
+    if ((f->fea_pe != 0 || f->view_pe != 0) && !allow_pe)
+      return fail(LRF_ERR_UNSUPPORTED, "positional encodings (fea_pe/view_pe > 0) are built for lrf_render only");
+    if (f->fea_pe > lrf::PE_MAX_FEA || f->view_pe > lrf::PE_MAX_VIEW)
+      return fail(LRF_ERR_UNSUPPORTED, "fea_pe / view_pe above 8 are not built");
   }
+  F.fea_pe = need_mlp ? f->fea_pe : 0;
+  F.view_pe = need_mlp ? f->view_pe : 0;
+  F.w3 = f->w3;
   F.z = f->z_vals;
   F.S = f->n_samples;
   if (need_table) {
@@ -179,15 +188,28 @@ const char* lrf_last_error(void) { return g_err; }
 
 size_t lrf_prepared_bytes(void) { return (size_t)lrf::PREP_BYTES; }
 
+size_t lrf_prepared_bytes_for(const LrfField* f) {
+  if (!f || f->fea_pe < 0 || f->view_pe < 0 || f->fea_pe > lrf::PE_MAX_FEA || f->view_pe > lrf::PE_MAX_VIEW) return 0;
+  if (f->fea_pe == 0 && f->view_pe == 0) return (size_t)lrf::PREP_BYTES;
+  return (size_t)lrf::pe_prepared_bytes(f->fea_pe);
+}
+
 int lrf_field_prepare(const LrfField* f, void* prepared, lrf_stream_t stream) {
   if (!f || !prepared) return fail(LRF_ERR_INVALID, "field or prepared is NULL");
   if ((uintptr_t)prepared & 15) return fail(LRF_ERR_INVALID, "prepared must be 16-byte aligned");
   if (f->app_dim != lrf::APP_DIM || f->featureC != lrf::FC || f->n_acomp != lrf::CA)
     return fail(LRF_ERR_UNSUPPORTED, "only app_dim=27 / featureC=128 / appearance_n_comp=24 are built");
-  if (f->fea_pe != 0 || f->view_pe != 0)
-    return fail(LRF_ERR_UNSUPPORTED, "positional encodings (fea_pe/view_pe > 0) are not built yet");
+  if (f->fea_pe < 0 || f->view_pe < 0 || f->fea_pe > lrf::PE_MAX_FEA || f->view_pe > lrf::PE_MAX_VIEW)
+    return fail(LRF_ERR_UNSUPPORTED, "fea_pe / view_pe must be in [0, 8]");
   if (!f->basis || !f->w1 || !f->b1 || !f->w2 || !f->b2 || !f->w3 || !f->b3)
     return fail(LRF_ERR_INVALID, "MLP / basis pointer is NULL");
+  if (f->fea_pe != 0 || f->view_pe != 0) {
+    if ((uintptr_t)prepared & 1023) return fail(LRF_ERR_INVALID, "the prepared block of a field with positional encodings must be 1024-byte aligned");
+    cudaError_t e = lrf::launch_prepare_pe(f->basis, f->w1, f->b1, f->w2, f->b2, f->w3, f->b3, f->fea_pe, f->view_pe,
+                                           static_cast<unsigned char*>(prepared), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "prepare_pe_kernel");
+    return LRF_OK;
+  }
   cudaError_t e = lrf::launch_prepare(f->basis, f->w1, f->b1, f->w2, f->b2, f->w3, f->b3,
                                       static_cast<unsigned char*>(prepared), (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "prepare_kernel");
@@ -199,8 +221,10 @@ int lrf_render(const LrfField* f, const void* prepared, const LrfBatch* b, const
   if (!b || !o) return fail(LRF_ERR_INVALID, "batch or outputs is NULL");
   if (!prepared) return fail(LRF_ERR_INVALID, "prepared is NULL (call lrf_field_prepare first)");
   lrf::FieldDev F;
-  int rc = make_field(f, true, true, prepared, F);
+  int rc = make_field(f, true, true, prepared, F, /*allow_pe=*/true);
   if (rc != LRF_OK) return rc;
+  if ((F.fea_pe || F.view_pe) && (!f->w3 || ((uintptr_t)prepared & 1023)))
+    return fail(LRF_ERR_INVALID, "positional encodings need w3 and a 1024-byte aligned prepared block");
   if (b->n_rays < 0) return fail(LRF_ERR_INVALID, "n_rays < 0");
   if (b->n_rays == 0) {
     // nothing to render; a rank with an empty shard must still publish its step to the peers
@@ -242,6 +266,7 @@ int lrf_render(const LrfField* f, const void* prepared, const LrfBatch* b, const
   B.exposure = b->exposure;
   B.accumulate = b->accumulate; B.finalize = b->finalize; B.white_bg = b->white_bg;
   B.floater_thresh = b->floater_thresh;
+  B.refine = b->refine;
   if (o->pix) {
     B.rgb = o->pix; B.depth = o->pix + 3; B.rgb_stride = 4; B.depth_stride = 4;
   } else {
@@ -281,7 +306,7 @@ int lrf_render(const LrfField* f, const void* prepared, const LrfBatch* b, const
   DevInfo d;
   rc = device_info(d);
   if (rc != LRF_OK) return rc;
-  const size_t smem = lrf::render_smem_bytes(F.S, B.floater_thresh > 0.0f, d.max_smem);
+  const size_t smem = lrf::render_smem_bytes(F.S, B.floater_thresh > 0.0f, d.max_smem, F.fea_pe > 0 || F.view_pe > 0);
   if ((long long)smem > d.max_smem)
     return fail(LRF_ERR_UNSUPPORTED, "sample table too long for the shared-memory budget");
   B.sched = d.sched + 2 * d.next;                                   // [ray counter, finished-CTA counter]
@@ -568,7 +593,7 @@ int lrf_launch_info(int32_t* n_sms, int32_t* threads_per_cta, int32_t* smem_byte
   if (rc != LRF_OK) return rc;
   if (n_sms) *n_sms = d.n_sms;
   if (threads_per_cta) *threads_per_cta = lrf::render_threads();
-  if (smem_bytes_per_cta) *smem_bytes_per_cta = (int32_t)lrf::render_smem_bytes(344, false, d.max_smem);
+  if (smem_bytes_per_cta) *smem_bytes_per_cta = (int32_t)lrf::render_smem_bytes(344, false, d.max_smem, false);
   return LRF_OK;
 }
 

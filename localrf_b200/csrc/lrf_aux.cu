@@ -236,6 +236,45 @@ __global__ void prepare_kernel(const float* __restrict__ basis, const float* __r
   for (int e = t; e < 4; e += stride) tail[TAIL_B3 + e] = e < 3 ? b3[e] : 0.0f;
 }
 
+// prepared block of a field with positional encodings (layout: lrf_common.cuh)
+__global__ void prepare_pe_kernel(const float* __restrict__ basis, const float* __restrict__ w1,
+                                  const float* __restrict__ b1, const float* __restrict__ w2,
+                                  const float* __restrict__ b2, const float* __restrict__ w3,
+                                  const float* __restrict__ b3, int fea_pe, int view_pe,
+                                  unsigned char* __restrict__ prep) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  auto put = [&](unsigned char* hi_img, unsigned char* lo_img, int off, float v) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    *reinterpret_cast<__nv_bfloat16*>(hi_img + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(lo_img + off) = lo;
+  };
+  for (int e = t; e < PE_N0 * K1; e += stride) {
+    const int n = e / K1, k = e - n * K1;
+    put(prep + PE_B0HI, prep + PE_B0LO, oper_offset(n, k, K1_CHUNKS), (n < APP_DIM && k < NF) ? basis[n * NF + k] : 0.0f);
+  }
+  for (int e = t; e < FC * FC; e += stride) {
+    const int n = e / FC, k = e - n * FC;
+    put(prep + PE_B2HI, prep + PE_B2LO, oper_offset(n, k, K2_CHUNKS), w2[n * FC + k]);
+  }
+  const int in_dim = pe_in_dim(fea_pe), nch = pe_chunks(fea_pe);
+  for (int e = t; e < nch * FC * PE_KC; e += stride) {
+    const int c = e / (FC * PE_KC), r = e - c * FC * PE_KC, n = r / PE_KC, kk = r - n * PE_KC;
+    const int k = c * PE_KC + kk;
+    unsigned char* img = prep + PE_W1 + (size_t)c * 2 * PE_WC_BYTES;
+    put(img, img + PE_WC_BYTES, oper_offset(n, kk, PE_KC / 8), k < in_dim ? w1[n * in_dim + k] : 0.0f);
+  }
+  float* tail = reinterpret_cast<float*>(prep + PE_TAIL);
+  const int w3_ld = FC + 3 * (1 + 2 * view_pe);
+  for (int e = t; e < FC; e += stride) { tail[TAIL_B1 + e] = b1[e]; tail[TAIL_B2 + e] = b2[e]; }
+  for (int e = t; e < 3 * W3_LD; e += stride) {
+    const int c = e / W3_LD, n = e - c * W3_LD;
+    tail[TAIL_W3 + e] = n < FC ? w3[c * w3_ld + n] : 0.0f;
+  }
+  for (int e = t; e < 4; e += stride) tail[TAIL_B3 + e] = e < 3 ? b3[e] : 0.0f;
+}
+
 __global__ void density_feature_kernel(const FieldDev F, const float* __restrict__ xyz,
                                        long long M, float* __restrict__ out) {
   long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -297,6 +336,13 @@ cudaError_t launch_prepare(const float* basis, const float* w1, const float* b1,
                            const float* b2, const float* w3, const float* b3, unsigned char* prep,
                            cudaStream_t stream) {
   prepare_kernel<<<64, 256, 0, stream>>>(basis, w1, b1, w2, b2, w3, b3, prep);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prepare_pe(const float* basis, const float* w1, const float* b1, const float* w2,
+                              const float* b2, const float* w3, const float* b3, int fea_pe, int view_pe,
+                              unsigned char* prep, cudaStream_t stream) {
+  prepare_pe_kernel<<<64, 256, 0, stream>>>(basis, w1, b1, w2, b2, w3, b3, fea_pe, view_pe, prep);
   return cudaGetLastError();
 }
 

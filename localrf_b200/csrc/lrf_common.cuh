@@ -38,6 +38,29 @@ constexpr int TAIL_FLOATS = TAIL_B3 + 4;
 constexpr int PREP_BYTES = PREP_TAIL + TAIL_FLOATS * 4;
 static_assert(PREP_BYTES % 16 == 0, "prepared block must be a multiple of 16 bytes");
 
+// ---- prepared block of a field WITH positional encodings (fea_pe > 0 or view_pe > 0) ------------------
+// basis_mat cannot be folded into layer 1 (the encoding sits between them), and layer 1's operand
+// [128][27 (1 + 2 fea_pe)] does not fit shared memory next to W2 for fea_pe up to 6, so it is cut into
+// K-chunks of 64 that the kernel streams per tile:
+//   B0 : basis_mat.weight[n][k], n < 32 (27 used), k < 80 (72 used)      bf16 hi | lo images
+//   B2 : mlp[2].weight                                                    bf16 hi | lo images (as above)
+//   tail (fp32, as above; W3 = the first 128 columns of mlp_view[0].weight, the view part is read from the
+//   module's own weight by the producers)
+//   W1 chunk c : mlp[0].weight[n][64 c .. 64 c + 63] (zero padded)       bf16 hi | lo images, 8 chunks per row
+constexpr int PE_N0 = 32;                                  // layer-0 (basis) N, padded
+constexpr int PE_B0_BYTES = 16 * K1_CHUNKS * PE_N0;        // one [32 x 80] operand = 5120
+constexpr int PE_KC = 64;                                  // K elements per streamed layer-1 chunk
+constexpr int PE_WC_BYTES = 16 * (PE_KC / 8) * 128;        // one [128 x 64] operand = 16384
+constexpr int PE_B0HI = 0, PE_B0LO = PE_B0_BYTES;
+constexpr int PE_B2HI = 2 * PE_B0_BYTES, PE_B2LO = PE_B2HI + OPER2_BYTES;
+constexpr int PE_TAIL = PE_B2LO + OPER2_BYTES;
+constexpr int PE_RESIDENT = PE_TAIL + TAIL_FLOATS * 4;     // what stays in shared memory (78 400 B)
+constexpr int PE_W1 = (PE_RESIDENT + 1023) & ~1023;        // chunk c at PE_W1 + c * 2 * PE_WC_BYTES (hi | lo)
+constexpr int PE_MAX_FEA = 8, PE_MAX_VIEW = 8;
+__host__ __device__ constexpr int pe_in_dim(int fea_pe) { return APP_DIM * (1 + 2 * fea_pe); }
+__host__ __device__ constexpr int pe_chunks(int fea_pe) { return (pe_in_dim(fea_pe) + PE_KC - 1) / PE_KC; }
+__host__ __device__ constexpr int pe_prepared_bytes(int fea_pe) { return PE_W1 + pe_chunks(fea_pe) * 2 * PE_WC_BYTES; }
+
 // byte offset of element (row, k) inside a core-matrix operand image with `chunks` k-chunks per row
 __host__ __device__ constexpr int oper_offset(int row, int k, int chunks) {
   return (((row >> 3) * chunks + (k >> 3)) * 8 + (row & 7)) * 16 + (k & 7) * 2;
@@ -58,6 +81,8 @@ struct FieldDev {
   int act;
   const float* z;
   int S;
+  int fea_pe, view_pe;        // positional encodings of the MLP (tensorBase.py:14-21,115-125); 0, 0 = the folded fast path
+  const float* w3;            // mlp_view[0].weight [3][128 + 3 (1 + 2 view_pe)] (the producers' view term)
 };
 
 struct BatchDev {
@@ -90,6 +115,7 @@ struct BatchDev {
   int rank;
   unsigned long long signal_seq, wait_seq;
   unsigned int* done_ctr;      // CTAs of this launch that have finished (library-owned, zeroed per launch)
+  int refine;                  // MLPRender_Fea_late_view's `refine` (tensorBase.py:118-124): 0 = zeros for the encoding
 };
 
 // ---- sampling helpers -------------------------------------------------------------------------

@@ -14,6 +14,7 @@ constexpr int TM_ACC1 = 0;       // fp32 accumulator of layer 1   [0,128)
 constexpr int TM_ACC2 = 128;     // fp32 accumulator of layer 2   [128,256)
 constexpr int TM_A2HI = 256;     // layer-2 A operand, bf16 hi: 128 K-elements = 64 columns
 constexpr int TM_A2LO = 320;     // layer-2 A operand, bf16 lo
+constexpr int TM_ACC0 = 384;     // (fields with positional encodings) fp32 accumulator of basis_mat, 32 columns
 // tcgen05 instruction descriptor, kind::f16: D=f32 (bit4), A=B=bf16 (bits 7,10), both K-major,
 // N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FC >> 3) << 17) |
@@ -118,6 +119,23 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(IDESC), "r"(accumulate)
       : "memory");
+}
+// the same two forms with an explicit instruction descriptor (other N, MN-major operands)
+__host__ __device__ constexpr uint32_t umma_idesc(int N, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_ss_id(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ts_id(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 // 32 lanes x 16 consecutive 32-bit columns from registers
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {

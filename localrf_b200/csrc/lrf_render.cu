@@ -67,6 +67,7 @@ struct Slot {                       // one ray in flight between a producer and 
   unsigned int rgb[3];              // sum of w * rgb, fixed point
   float acc;
   float depth;                      // final depth of the ray (for the fused pixel exchange)
+  float vterm[3];                   // (fields with view encodings) W3[:, 128:] . [vd, PE(vd)]
   long long ray;
   int pending;                      // 1 (open token) + rows submitted and not yet composited
   int state;                        // 0 free, 1 active
@@ -94,6 +95,7 @@ struct RayRec {
 
 struct Ctrl {                       // CTA control block in shared memory
   unsigned long long bar_w, full[2], mma1, a2rdy, mma2;
+  unsigned long long mma0, xrdy[2], xfree[2], wrdy;   // fields with positional encodings (PE pipeline)
   uint32_t tmem;
   unsigned int released;            // tiles whose A1 buffer + row metadata may be overwritten
   unsigned int cursor;              // rows handed out so far (tile = cursor >> 7)
@@ -108,11 +110,12 @@ struct SmemV3 {
   int per_prod;                     // bytes of one producer's queue (+ alpha table)
 };
 
-__host__ __device__ inline SmemV3 smem_v3(int S, bool floater, int nprod) {
+constexpr int PE_WBUF = (PE_RESIDENT + 1023) & ~1023;     // offset of the streamed layer-1 chunk inside the prep region
+__host__ __device__ inline SmemV3 smem_v3(int S, bool floater, int nprod, bool pe = false) {
   SmemV3 L;
   int off = 0;
   const int Sp = (S + 3) & ~3;
-  L.prep = off;   off += PREP_BYTES;
+  L.prep = off;   off += pe ? PE_WBUF + 2 * PE_WC_BYTES : PREP_BYTES;
   off = (off + 1023) & ~1023;
   L.a1 = off;     off += 2 * 2 * OPER1_BYTES;          // two A1 tiles (hi + lo each)
   L.mslot = off;  off += 2 * TM;                        // per-row slot id (u8), two tiles
@@ -405,11 +408,15 @@ __device__ __forceinline__ void process_step(const ProdCtx& P, const FieldDev& F
 }
 
 // =================================================================================================
+// PE = the field has positional encodings (fea_pe > 0 or view_pe > 0): basis_mat is its own tensor-core
+// product (layer 0), the consumers build the encoded layer-1 input chunk by chunk in TMEM, layer 1's weight
+// operand is streamed by TMA in K-chunks of 64.  PE = false is the reference-default fast path (folded basis).
+template <bool PE>
 __global__ void __launch_bounds__(THREADS, 1)
-render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
+render_kernel_t(const FieldDev F, const BatchDev B, const int nprod) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const bool floater = B.floater_thresh > 0.0f;
-  const SmemV3 L = smem_v3(F.S, floater, nprod);
+  const SmemV3 L = smem_v3(F.S, floater, nprod, PE);
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem + L.ctrl);
   Slot* slots = reinterpret_cast<Slot*>(smem + L.slots);
   float* z_s = reinterpret_cast<float*>(smem + L.z);
@@ -424,9 +431,15 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
     mbar_init(smem_u32(&ctrl->mma1), 1);
     mbar_init(smem_u32(&ctrl->a2rdy), TM * N_CONS / 4);
     mbar_init(smem_u32(&ctrl->mma2), 1);
+    if (PE) {
+      mbar_init(smem_u32(&ctrl->mma0), 1);
+      mbar_init(smem_u32(&ctrl->xrdy[0]), TM); mbar_init(smem_u32(&ctrl->xrdy[1]), TM);
+      mbar_init(smem_u32(&ctrl->xfree[0]), 1); mbar_init(smem_u32(&ctrl->xfree[1]), 1);
+      mbar_init(smem_u32(&ctrl->wrdy), 1);
+    }
     ctrl->cursor = 0; ctrl->prod_done = 0; ctrl->draw_done = 0; ctrl->n_tiles_final = 0; ctrl->done = 0;
     ctrl->released = 0;
-    constexpr uint32_t bytes = PREP_BYTES;
+    constexpr uint32_t bytes = PE ? PE_RESIDENT : PREP_BYTES;
     mbar_expect_tx(smem_u32(&ctrl->bar_w), bytes);
     constexpr uint32_t CH = 32768;
     for (uint32_t o = 0; o < bytes; o += CH)
@@ -509,6 +522,27 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
         slot->rgb[0] = slot->rgb[1] = slot->rgb[2] = 0u;
         slot->ray = ray;
         slot->pending = 1;
+      }
+      if (PE) {
+        // view term of layer 3 (tensorBase.py:126-131): W3[:, 128:] . [vd, sin(vd 2^f), cos(vd 2^f)], d-major f-minor
+        const int V = F.view_pe, nv = 3 * (1 + 2 * V), ld = FC + nv;
+        float vt[3] = {0.0f, 0.0f, 0.0f};
+        for (int j = lane; j < nv; j += 32) {
+          float v;
+          if (j < 3) v = R.vd[j];
+          else {
+            const int e = (j - 3) % (3 * V), d = e / V, f = e - d * V;
+            const float ang = R.vd[d] * (float)(1 << f);
+            v = (j - 3) < 3 * V ? sinf(ang) : cosf(ang);
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) vt[c] = fmaf(__ldg(F.w3 + c * ld + FC + j), v, vt[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vt[c] = warp_sum(vt[c]);
+        if (lane == 0) { slot->vterm[0] = vt[0]; slot->vterm[1] = vt[1]; slot->vterm[2] = vt[2]; }
+      }
+      if (lane == 0) {
         __threadfence_block();
         *reinterpret_cast<volatile int*>(&slot->state) = 1;
       }
@@ -666,6 +700,7 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
   } else if (warp == W_ISSUE) {
     // ======================================= MMA ISSUER ==========================================
     const uint32_t prep_a = smem_u32(smem + L.prep);
+    uint32_t wpar = 0, xuse[2] = {0u, 0u};            // PE pipeline: parity of wrdy, uses of the two input-chunk buffers
     mbar_wait(smem_u32(&ctrl->bar_w), 0);
     for (unsigned int T = 0;; ++T) {
       const int b = (int)(T & 1);
@@ -675,7 +710,58 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
             T >= *reinterpret_cast<volatile unsigned int*>(&ctrl->n_tiles_final)) { stop = true; break; }
       }
       if (stop) break;
-      if (lane == 0) {
+      if (PE) {
+        // layer 0: acc0[128 x 32] = products x basis^T (three bf16 products), then layer 1 chunk by chunk
+        const int nch = pe_chunks(F.fea_pe);
+        const uint32_t wbuf = prep_a + PE_WBUF;
+        const unsigned char* w1_g = reinterpret_cast<const unsigned char*>(F.prep) + PE_W1;
+        if (lane == 0) {
+          mbar_expect_tx(smem_u32(&ctrl->wrdy), 2 * PE_WC_BYTES);                 // chunk 0 streams in under layer 0
+          tma_bulk_g2s(wbuf, w1_g, 2 * PE_WC_BYTES, smem_u32(&ctrl->wrdy));
+          tc_fence_after();
+          const uint32_t a1 = smem_u32(smem + L.a1 + b * (2 * OPER1_BYTES));
+          const uint32_t sbo = (uint32_t)K1_CHUNKS * 128u, id0 = umma_idesc(PE_N0);
+          uint32_t accf = 0;
+          for (int ks = 0; ks < K1 / 16; ++ks) {
+            const uint32_t ko = (uint32_t)ks * 256u;
+            const uint64_t ah = umma_desc(a1 + ko, 128u, sbo), al = umma_desc(a1 + OPER1_BYTES + ko, 128u, sbo);
+            const uint64_t bh = umma_desc(prep_a + PE_B0HI + ko, 128u, sbo), bl = umma_desc(prep_a + PE_B0LO + ko, 128u, sbo);
+            umma_ss_id(tmem + TM_ACC0, ah, bh, id0, accf);
+            umma_ss_id(tmem + TM_ACC0, ah, bl, id0, 1u);
+            umma_ss_id(tmem + TM_ACC0, al, bh, id0, 1u);
+            accf = 1u;
+          }
+          umma_commit(smem_u32(&ctrl->mma0));
+        }
+        __syncwarp();
+        for (int c = 0; c < nch; ++c) {
+          const int xb = c & 1;
+          mbar_wait(smem_u32(&ctrl->wrdy), wpar); wpar ^= 1u;                      // weight chunk c is in shared memory
+          mbar_wait(smem_u32(&ctrl->xrdy[xb]), xuse[xb] & 1u);                     // input chunk c is in TMEM
+          if (lane == 0) {
+            tc_fence_after();
+            const uint32_t sbo = (uint32_t)(PE_KC / 8) * 128u, id1 = umma_idesc(FC);
+            const uint32_t a_hi = tmem + TM_A2HI + xb * 32, a_lo = tmem + TM_A2LO + xb * 32;
+            for (int ks = 0; ks < PE_KC / 16; ++ks) {
+              const uint32_t ko = (uint32_t)ks * 256u, kc = (uint32_t)ks * 8u;
+              const uint64_t bh = umma_desc(wbuf + ko, 128u, sbo), bl = umma_desc(wbuf + PE_WC_BYTES + ko, 128u, sbo);
+              const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
+              umma_ts_id(tmem + TM_ACC1, a_hi + kc, bh, id1, first);
+              umma_ts_id(tmem + TM_ACC1, a_hi + kc, bl, id1, 1u);
+              umma_ts_id(tmem + TM_ACC1, a_lo + kc, bh, id1, 1u);
+            }
+            umma_commit(smem_u32(&ctrl->xfree[xb]));
+          }
+          __syncwarp();
+          mbar_wait(smem_u32(&ctrl->xfree[xb]), xuse[xb] & 1u);                    // chunk c consumed: buffers reusable
+          xuse[xb]++;
+          if (c + 1 < nch && lane == 0) {
+            mbar_expect_tx(smem_u32(&ctrl->wrdy), 2 * PE_WC_BYTES);
+            tma_bulk_g2s(wbuf, w1_g + (size_t)(c + 1) * 2 * PE_WC_BYTES, 2 * PE_WC_BYTES, smem_u32(&ctrl->wrdy));
+          }
+        }
+        if (lane == 0) { tc_fence_after(); umma_commit(smem_u32(&ctrl->mma1)); }   // layer 1 complete
+      } else if (lane == 0) {
         tc_fence_after();
         const uint32_t a1 = smem_u32(smem + L.a1 + b * (2 * OPER1_BYTES));
         const uint32_t sbo = (uint32_t)K1_CHUNKS * 128u;
@@ -697,8 +783,8 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
       mbar_wait(smem_u32(&ctrl->a2rdy), T & 1);       // layer-2 A operand is in TMEM
       if (lane == 0) {
         tc_fence_after();
-        issue_layer_ts(tmem + TM_ACC2, tmem + TM_A2HI, tmem + TM_A2LO, prep_a + PREP_B2HI,
-                       prep_a + PREP_B2LO, FC / 16, K2_CHUNKS, smem_u32(&ctrl->mma2));
+        issue_layer_ts(tmem + TM_ACC2, tmem + TM_A2HI, tmem + TM_A2LO, prep_a + (PE ? PE_B2HI : PREP_B2HI),
+                       prep_a + (PE ? PE_B2LO : PREP_B2LO), FC / 16, K2_CHUNKS, smem_u32(&ctrl->mma2));
       }
       __syncwarp();
     }
@@ -708,7 +794,8 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
     const int chalf = (warp - W_CONS) >> 2, col0 = chalf * CONS_COLS;     // this thread's accumulator columns
     float* part_s = reinterpret_cast<float*>(smem + L.part);
     const uint32_t t_row = tmem + ((uint32_t)(q4 * 32) << 16);
-    const float* tail = reinterpret_cast<const float*>(smem + L.prep + PREP_TAIL);
+    const float* tail = reinterpret_cast<const float*>(smem + L.prep + (PE ? PE_TAIL : PREP_TAIL));
+    uint32_t xuse[2] = {0u, 0u};
     const float* b1_s = tail + TAIL_B1;
     const float* b2_s = tail + TAIL_B2;
     const float* W3_s = tail + TAIL_W3;
@@ -717,7 +804,7 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
     for (unsigned int T = 0;; ++T) {
       const int b = (int)(T & 1);
       bool stop = false;
-      while (!mbar_try(smem_u32(&ctrl->mma1), T & 1)) {
+      while (!mbar_try(smem_u32(PE ? &ctrl->mma0 : &ctrl->mma1), T & 1)) {
         if (*reinterpret_cast<volatile unsigned int*>(&ctrl->done) &&
             T >= *reinterpret_cast<volatile unsigned int*>(&ctrl->n_tiles_final)) { stop = true; break; }
       }
@@ -726,10 +813,53 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
       // row metadata -> registers, then the A1 tile (and its metadata) may be rewritten
       const int my_slot = smem[L.mslot + b * TM + row];
       const float my_w = reinterpret_cast<const float*>(smem + L.mw)[b * TM + row];
-      asm volatile("bar.sync 2, %0;" ::"n"(N_CONS * 32) : "memory");   // MMA1(T) done + all metadata read ->
+      asm volatile("bar.sync 2, %0;" ::"n"(N_CONS * 32) : "memory");   // first MMA of tile T done + all metadata read ->
       if (ctid == 0) {                                  // the A1 buffer of tile T is free again
         __threadfence_block();
         *reinterpret_cast<volatile unsigned int*>(&ctrl->released) = T + 1u;
+      }
+      if (PE) {
+        // -- layer-0 epilogue: the 27 basis features; encoded layer-1 input, 64 columns at a time ------------
+        // x = [a, sin(a_d 2^f) (d-major, f-minor), cos(...)]   (tensorBase.py:14-21,115-125); zeros when !refine
+        float a[32];
+        tmem_ld32(t_row + (uint32_t)TM_ACC0, a);
+        const int Fp = F.fea_pe, nsin = APP_DIM * Fp, nch = pe_chunks(Fp);
+        if (chalf == 0) {
+          for (int c = 0; c < nch; ++c) {
+            const int xb = c & 1;
+            if (xuse[xb] > 0) mbar_wait(smem_u32(&ctrl->xfree[xb]), (xuse[xb] - 1u) & 1u);   // previous occupant consumed
+            tc_fence_after();
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {                       // 32 columns -> 16 packed words hi, 16 lo
+              uint32_t hi[16], lo[16];
+#pragma unroll 1
+              for (int j2 = 0; j2 < 16; ++j2) {
+                float v2[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int j = c * PE_KC + h * 32 + 2 * j2 + u;
+                  float v = 0.0f;
+                  if (j < APP_DIM) v = a[j];
+                  else if (B.refine && j < APP_DIM + 2 * nsin) {
+                    const int e = (j - APP_DIM) % nsin, d = e / Fp, f = e - d * Fp;
+                    const float ang = a[d] * (float)(1 << f);
+                    v = (j - APP_DIM) < nsin ? sinf(ang) : cosf(ang);
+                  }
+                  v2[u] = v;
+                }
+                split2(v2[0], v2[1], hi[j2], lo[j2]);
+              }
+              tmem_st16(t_row + (uint32_t)(TM_A2HI + xb * 32 + h * 16), hi);
+              tmem_st16(t_row + (uint32_t)(TM_A2LO + xb * 32 + h * 16), lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&ctrl->xrdy[xb]));
+            xuse[xb]++;
+          }
+        }
+        mbar_wait(smem_u32(&ctrl->mma1), T & 1);         // every chunk of layer 1 has been accumulated
+        tc_fence_after();
       }
       // -- epilogue 1: h1 = relu(acc1 + b1) -> bf16 hi/lo, layer 2's A operand in TMEM -------------
 #pragma unroll 1
@@ -789,8 +919,9 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           float sc = pa[c] + pb[c];
-          sc += W3_s[c * W3_LD + FC] * sl->vd[0] + W3_s[c * W3_LD + FC + 1] * sl->vd[1] +
-                W3_s[c * W3_LD + FC + 2] * sl->vd[2];
+          if (PE) sc += sl->vterm[c];
+          else sc += W3_s[c * W3_LD + FC] * sl->vd[0] + W3_s[c * W3_LD + FC + 1] * sl->vd[1] +
+                     W3_s[c * W3_LD + FC + 2] * sl->vd[2];
           sc += b3_s[c];
           sc = __fdiv_rn(1.0f, 1.0f + expf(-sc));
           atomicAdd(&sl->rgb[c], __float2uint_rn(my_w * sc * FIX_SCALE));
@@ -822,36 +953,38 @@ render_kernel(const FieldDev F, const BatchDev B, const int nprod) {
 // ---- host-side launcher --------------------------------------------------------------------------
 int render_threads() { return THREADS; }
 
-static int pick_nprod(int S, bool floater, int max_smem) {
+static int pick_nprod(int S, bool floater, int max_smem, bool pe = false) {
   int cap = MAX_PROD;
   if (const char* e = getenv("LRF_NPROD")) {      // tuning / debugging knob
     const int v = atoi(e);
     if (v >= 1 && v < cap) cap = v;
   }
   for (int n = cap; n >= 1; --n)
-    if (smem_v3(S, floater, n).total <= max_smem) return n;
+    if (smem_v3(S, floater, n, pe).total <= max_smem) return n;
   return 0;
 }
 
-size_t render_smem_bytes(int S, bool floater, int max_smem) {
-  const int n = pick_nprod(S, floater, max_smem);
-  return (size_t)smem_v3(S, floater, n ? n : 1).total;
+size_t render_smem_bytes(int S, bool floater, int max_smem, bool pe) {
+  const int n = pick_nprod(S, floater, max_smem, pe);
+  return (size_t)smem_v3(S, floater, n ? n : 1, pe).total;
 }
 
 cudaError_t launch_render(const FieldDev& F, const BatchDev& B, int n_sms, int max_smem,
                           cudaStream_t stream) {
   const bool floater = B.floater_thresh > 0.0f;
-  const int nprod = pick_nprod(F.S, floater, max_smem);
+  const bool pe = F.fea_pe > 0 || F.view_pe > 0;
+  const int nprod = pick_nprod(F.S, floater, max_smem, pe);
   if (nprod < 1) return cudaErrorInvalidConfiguration;
-  const size_t smem = (size_t)smem_v3(F.S, floater, nprod).total;
-  static size_t configured[64] = {0};   // per device: the attribute belongs to the device's context
+  const size_t smem = (size_t)smem_v3(F.S, floater, nprod, pe).total;
+  static size_t configured[2][64] = {{0}, {0}};   // per kernel, per device: the attribute belongs to the device's context
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev >= 0 && dev < 64 && smem > configured[dev]) {
-    e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (dev >= 0 && dev < 64 && smem > configured[pe][dev]) {
+    e = pe ? cudaFuncSetAttribute(render_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+           : cudaFuncSetAttribute(render_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[dev] = smem;
+    configured[pe][dev] = smem;
   }
   e = cudaMemsetAsync(B.sched, 0, 2 * sizeof(unsigned long long), stream);   // ray counter + finished-CTA counter
   if (e != cudaSuccess) return e;
@@ -859,7 +992,8 @@ cudaError_t launch_render(const FieldDev& F, const BatchDev& B, int n_sms, int m
   long long want = (B.n_rays + 7) / 8;
   int grid = (int)(want < n_sms ? want : n_sms);
   if (grid < 1) grid = 1;
-  render_kernel<<<grid, THREADS, smem, stream>>>(F, B, nprod);
+  if (pe) render_kernel_t<true><<<grid, THREADS, smem, stream>>>(F, B, nprod);
+  else render_kernel_t<false><<<grid, THREADS, smem, stream>>>(F, B, nprod);
   return cudaGetLastError();
 }
 

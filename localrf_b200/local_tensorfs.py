@@ -453,7 +453,7 @@ class LocalTensorfs(torch.nn.Module):
                    None if cam2world is None else (id(cam2world), cam2world._version),
                    None if world2rf is None else id(world2rf),
                    None if blending_weights is None else (id(blending_weights), blending_weights._version),
-                   id(self.blending_weights), len(self.tensorfs), exchange is not None, dev)
+                   id(self.blending_weights), len(self.tensorfs), exchange is not None, bool(self.is_refining), dev)
             plans = self.__dict__.setdefault("_plans", {})
             plan = plans.get(key)
             if plan is not None and plan.valid():
@@ -659,6 +659,7 @@ class LocalTensorfs(torch.nn.Module):
                         b.exposure = exposure.data_ptr() + 36 * v_lo
                     b.white_bg = int(bool(white_bg) or bool(is_train and torch.rand((1,)) < 0.5))
                     b.floater_thresh = float(floater_thresh)
+                    b.refine = int(bool(self.is_refining))        # local_tensorfs.py:463
                     o = _lib.LrfOutputs()
                     if pix is not None:
                         o.pix = pix.data_ptr() + 16 * lo

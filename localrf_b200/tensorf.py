@@ -531,11 +531,16 @@ class TensorBase(torch.nn.Module):
         return fs, self._prepared
 
     def prepare(self, field_struct):
-        """(Re)builds the folded / re-laid-out MLP block the kernel stages into shared memory."""
+        """(Re)builds the folded / re-laid-out MLP block the kernel stages into shared memory (for a field with
+        positional encodings: the separate basis / layer-1 operand images, 1024-byte aligned for TMA)."""
         dev = self.basis_mat.weight.device
-        if self._prepared is None or self._prepared.device != dev:
-            n = _lib.lib().lrf_prepared_bytes()
-            self._prepared = torch.empty(n, dtype=torch.uint8, device=dev)
+        n = _lib.lib().lrf_prepared_bytes_for(C.byref(field_struct))
+        if n == 0:
+            raise NotImplementedError("localrf_b200: fea_pe / view_pe above 8 are not built")
+        if self._prepared is None or self._prepared.device != dev or self._prepared.numel() != n:
+            raw = torch.empty(n + 1024, dtype=torch.uint8, device=dev)
+            off = (-raw.data_ptr()) % 1024
+            self._prepared = raw[off:off + n]
         _lib.check(_lib.lib().lrf_field_prepare(C.byref(field_struct), _ptr(self._prepared),
                                                 _stream(dev)))
         return self._prepared
@@ -544,6 +549,8 @@ class TensorBase(torch.nn.Module):
         """basis_mat + renderModule on explicit plane x line products [M,72] and normalised view
         directions [M,3] -> rgb [M,3]; the tensor-core MLP of the render kernel on its own."""
         _require_cuda(products, "products")
+        if self.fea_pe or self.view_pe:
+            raise NotImplementedError("localrf_b200: the stand-alone MLP entry (lrf_mlp_forward) covers pe = 0")
         dev = products.device
         x = products.detach().to(torch.float32).contiguous()
         v = viewdirs.detach().to(dev, torch.float32).contiguous()
@@ -568,6 +575,7 @@ class TensorBase(torch.nn.Module):
         wants_grad = self._wants_grad(rays_chunk, *self.parameters())
         fused_grad = (wants_grad and floater_thresh == 0 and not return_weights and stats is None
                       and rays_chunk.dim() == 2 and rays_chunk.shape[1] == 6
+                      and self.fea_pe == 0 and self.view_pe == 0       # the fused backward covers pe = 0
                       and os.environ.get("LRF_TRAIN_PATH", "fused") != "composed")
         if not self.fused_supported() or (wants_grad and not fused_grad):
             return self._forward_autograd(rays_chunk, white_bg, is_train, N_samples, refine,
@@ -585,7 +593,7 @@ class TensorBase(torch.nn.Module):
             self.last_weights = None
             return _RenderFn.apply(self, z, bg, rays_chunk, *self._grad_params())
         rays = rays_chunk.detach()[:, :6].contiguous()
-        return self._render_fused(rays, z, bg, floater_thresh, return_weights, stats)
+        return self._render_fused(rays, z, bg, floater_thresh, return_weights, stats, refine)
 
     def _grad_params(self):
         """Parameters in the order _RenderFn.backward returns their gradients."""
@@ -612,7 +620,7 @@ class TensorBase(torch.nn.Module):
             self.__dict__["_bprep_memo"] = memo
         return memo[1]
 
-    def _render_fused(self, rays, z, bg, floater_thresh, return_weights, stats):
+    def _render_fused(self, rays, z, bg, floater_thresh, return_weights, stats, refine=True):
         """One lrf_render launch on explicit rays [n,6] (contiguous fp32) -> (rgb [n,3], depth [n])."""
         dev, n = rays.device, rays.shape[0]
         with torch.cuda.device(dev):
@@ -626,6 +634,7 @@ class TensorBase(torch.nn.Module):
             b.n_views = 1
             b.white_bg = int(bg)
             b.floater_thresh = float(floater_thresh)
+            b.refine = int(bool(refine))
             o = _lib.LrfOutputs()
             o.rgb, o.depth = rgb.data_ptr(), depth.data_ptr()
             if weights is not None:
@@ -638,10 +647,11 @@ class TensorBase(torch.nn.Module):
         return rgb, depth
 
     def fused_supported(self):
-        """Configurations the fused kernel covers (the reference defaults).  Anything else that is
-        valid for MLP_Fea_late_view -- positional encodings -- renders through the composed path
-        below (CUDA lookups + torch MLP), on the GPU, at the reference's semantics."""
-        return self.fea_pe == 0 and self.view_pe == 0 and self.app_dim == 27 and self.featureC == 128
+        """Configurations the fused forward kernel covers: the reference defaults (pe = 0: basis folded
+        into layer 1) and positional encodings up to 8 frequencies (a second instantiation of the kernel:
+        basis as its own tensor-core product, encoded input built in TMEM, layer-1 weights streamed).
+        The fused BACKWARD covers pe = 0; fields with encodings train through the composed path."""
+        return self.app_dim == 27 and self.featureC == 128 and 0 <= self.fea_pe <= 8 and 0 <= self.view_pe <= 8
 
     def _forward_autograd(self, rays_chunk, white_bg, is_train, N_samples, refine, floater_thresh,
                           return_weights, z_vals):

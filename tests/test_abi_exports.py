@@ -35,7 +35,7 @@ def test_struct_sizes_match_c_layout():
     # natural-alignment layouts of the header structs (x86-64)
     # + n_peers (padded), peer_pix[16], mc_pix, peer_flags[16], rank (padded), signal_seq, wait_seq
     assert C.sizeof(_lib.LrfOutputs) == 7 * 8 + 8 + 16 * 8 + 8 + 16 * 8 + 8 + 16
-    assert C.sizeof(_lib.LrfBatch) == 120
+    assert C.sizeof(_lib.LrfBatch) == 128                            # 116 + refine (int32), padded
     assert C.sizeof(_lib.LrfField) % 8 == 0
     # ... and the compiled library agrees with every ctypes mirror (checked again at load time)
     L = _lib.lib()

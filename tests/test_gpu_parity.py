@@ -109,24 +109,62 @@ def test_small_fields_vs_reference_golden(name, cases):
     ("refine", dict(refine=True, floater_thresh=0.5)),
     ("norefine", dict(refine=False)),
 ])
-def test_positional_encodings_render_through_composed_path(case, kw):
-    """fea_pe = view_pe = 2 on a [40,52,64] grid: not covered by the fused kernel, rendered by the
-    composed path (CUDA lookups + torch MLP) -- against the reference golden.  The raw C ABI reports
-    the configuration as unsupported instead of approximating it."""
+def test_positional_encodings_fused_vs_reference_golden(case, kw):
+    """fea_pe = view_pe = 2 on a [40,52,64] grid through the FUSED kernel (the instantiation with the basis as
+    its own tensor-core product, the encoded layer-1 input built in TMEM and layer-1 weights streamed by TMA)
+    against the reference golden, refine on / off; the composed path must agree too, and the raw C ABI accepts
+    the configuration."""
     import ctypes as C
     from gpu_helpers import module_from_golden
     from localrf_b200 import _lib
     g = load_golden("aniso_pe")
     m = module_from_golden(g)
-    assert not m.fused_supported()
+    assert m.fused_supported()
     rgb, depth, w = _run(m, g, case, **kw)
     assert rel_err(rgb, g[f"{case}.rgb"]) < TOL
     assert rel_err(depth, g[f"{case}.depth"]) < TOL
     assert rel_err(w, g[f"{case}.weights"], floor=WFLOOR) < TOL
-    fs, keep = m._field_struct(torch.from_numpy(g[f"{case}.z"]).cuda())
-    prep = torch.empty(_lib.lib().lrf_prepared_bytes(), dtype=torch.uint8, device="cuda")
-    rc = _lib.lib().lrf_field_prepare(C.byref(fs), C.c_void_p(prep.data_ptr()), None)
-    assert rc == -2 and b"positional" in _lib.lib().lrf_last_error()
+    rays = torch.from_numpy(g["rays"]).cuda()
+    z = torch.from_numpy(g[f"{case}.z"]).cuda()
+    with torch.no_grad():                                   # the composed path (CUDA lookups + torch MLP module)
+        rgb_c, depth_c = m._forward_autograd(rays, True, False, -1, kw.get("refine", True),
+                                             kw.get("floater_thresh", 0), False, z)
+    assert rel_err(rgb_c.cpu().numpy(), g[f"{case}.rgb"]) < TOL
+    fs, keep = m._field_struct(z)
+    n = _lib.lib().lrf_prepared_bytes_for(C.byref(fs))
+    assert n > _lib.lib().lrf_prepared_bytes()
+    prep = torch.empty(n + 1024, dtype=torch.uint8, device="cuda")
+    off = (-prep.data_ptr()) % 1024
+    assert _lib.lib().lrf_field_prepare(C.byref(fs), C.c_void_p(prep.data_ptr() + off), None) == 0
+    # stand-alone entries that only exist for pe = 0 still say so instead of approximating
+    fs2, _ = m._field_struct(z)
+    assert _lib.lib().lrf_field_prepare_backward(C.byref(fs2), C.c_void_p(prep.data_ptr() + off), None) == -2
+
+
+@pytest.mark.parametrize("fea_pe,view_pe", [(6, 6), (0, 4), (3, 0), (1, 1), (8, 8)])
+def test_positional_encodings_fused_vs_oracle(fea_pe, view_pe):
+    """Other encoding widths (one to six streamed layer-1 chunks, view-only, feature-only) against the pinned
+    oracle on seeded inputs, refine on and off, with and without the floater filter."""
+    import localrf_b200 as L
+    from gpu_helpers import AABB, field_kwargs
+    torch.manual_seed(60 + fea_pe * 10 + view_pe)
+    sc = dict(app_dim=27, density_shift=-5.0, distance_scale=25.0, rayMarch_weight_thres=1e-3,
+              view_pe=view_pe, fea_pe=fea_pe, featureC=128, step_ratio=0.5, fea2denseAct="softplus")
+    m = L.TensorVMSplit("cuda", AABB.clone().cuda(), [36, 44, 40], **field_kwargs(sc))
+    with torch.no_grad():                                   # features of order 1 so that sin / cos are exercised
+        m.basis_mat.weight.mul_(20.0)
+    fd = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    fd.update(sc); fd["gridSize"] = [36, 44, 40]
+    f = orc.Field(fd)
+    gen = torch.Generator().manual_seed(61)
+    rays = torch.cat([0.3 * torch.randn(700, 3, generator=gen), torch.randn(700, 3, generator=gen)], -1)
+    z = orc.sample_table(f.n_samples())
+    for refine, thr in ((True, 0.0), (False, 0.0), (True, 0.5)):
+        ref = orc.field_forward(f, rays.numpy(), z, floater_thresh=thr, refine=refine)
+        with torch.no_grad():
+            rgb, depth = m(rays.cuda(), floater_thresh=thr, refine=refine)
+        assert rel_err(rgb.cpu().numpy(), ref["rgb"]) < TOL, (refine, thr)
+        assert rel_err(depth.cpu().numpy(), ref["depth"]) < TOL, (refine, thr)
 
 
 def test_anisotropic_grid_vs_oracle():
