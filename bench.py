@@ -459,7 +459,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "distB", "incoherent", "cfg3", "cfg5"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong", "frame"])
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
-    ap.add_argument("--lag", type=int, default=1, help="fused exchange: steps of slack between a rank and its "
+    ap.add_argument("--lag", type=int, default=3, help="fused exchange: steps of slack between a rank and its "
                     "slowest peer (0 = same-step barrier; L >= 1: step s waits for the peers' step s-1-L, the "
                     "gathered image of step s-1-L is complete after the launch of step s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -166,10 +166,7 @@ def render_sharded(local_tensorfs, ray_ids, view_ids, W, H, group=None, exchange
         return gather_pixels(rgb, depth, n, group)
     if n > exchange.max_rays:
         raise ValueError(f"batch of {n} rays exceeds the exchange buffer ({exchange.max_rays})")
-    if hi > lo:
-        local_tensorfs(ray_ids[lo:hi], view_ids, W, H, exchange=(exchange, lo), **kw)
-    else:
-        exchange.skip_step(C.c_void_p(torch.cuda.current_stream(exchange.device).cuda_stream))
+    local_tensorfs(ray_ids[lo:hi], view_ids, W, H, exchange=(exchange, lo), **kw)   # (an empty shard only signals)
     full = exchange.gathered(n)
     return full[:, :3], full[:, 3]
 

@@ -446,6 +446,11 @@ class LocalTensorfs(torch.nn.Module):
                 raise RuntimeError("localrf_b200: the scene model is on the CPU; the render path runs "
                                    "only on a CUDA device (there is no CPU fallback)")
         n = ray_ids.shape[0]
+        if n == 0:                                        # an empty batch / shard: nothing to launch
+            if exchange is not None:
+                exchange[0].skip_step(_stream(dev))       # ... but the peers still need this rank's step flag
+            return (torch.empty(0, 3, device=dev), torch.empty(0, device=dev), torch.empty(0, 3, device=dev),
+                    torch.empty(0, 2, dtype=torch.int64, device=dev))
         if not is_train and not torch.is_grad_enabled():
             # eval fast path: reuse the resolved plan of an identical earlier call
             vkey = (id(view_ids), view_ids._version) if torch.is_tensor(view_ids) else tuple(view_ids)

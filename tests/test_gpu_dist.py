@@ -17,7 +17,9 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev,
+                            timeout=datetime.timedelta(seconds=90))       # a rank that dies must not stall its peer for minutes
     res = {}
     try:
         import bench
@@ -79,7 +81,7 @@ def test_render_sharded_equals_unsharded(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = dict(q.get(timeout=600) for _ in range(world))
+    results = dict(q.get(timeout=240) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
     print(results)
