@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "../../include/localrf_b200.h"
 #include "lrf_common.cuh"
@@ -86,8 +87,12 @@ struct DevInfo {
 };
 constexpr unsigned int SCHED_RING = 256;
 
+// per-device launch resources, process-global (one ring of launch counters per device, allocated on first
+// use by whichever host thread gets there first; the autograd engine's worker threads share it)
 int device_info(DevInfo& d) {
-  static thread_local DevInfo cache[64];
+  static DevInfo cache[64];
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
