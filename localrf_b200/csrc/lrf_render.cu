@@ -6,29 +6,34 @@
 // clamp.  Replaces TensorBase.forward (models/tensorBase.py:567-636) and the per-field body of
 // LocalTensorfs.forward (local_tensorfs.py:397-497).
 //
-// One persistent CTA per SM, 16 warps in three roles that only meet through mbarriers:
+// One persistent CTA per SM, 16 warps (512 threads; LRF_THREADS) in three roles that only meet through
+// mbarriers and a few shared-memory counters:
 //
-//   producers (up to 11 warps)  each takes one ray at a time from a global counter (dynamic
+//   producers (warps 0 .. W_ISSUE-1: 11)  each takes one ray at a time from a global counter (dynamic
 //       scheduling: no wave quantisation of a 4096-ray batch).  March: lane = sample, 32 samples
 //       per step, transmittance by a warp-shuffle product scan with a carried prefix.  Samples
-//       with w > threshold go to a small per-warp queue; every 32 of them are gathered
-//       (lane = sample: 3 planes x 4 texels x 96 B + 3 lines, 72 products), split into bf16
-//       hi/lo and written as one ROW of the current 128-row A tile in shared memory (K-major
-//       8x8 core matrices).  Rows are handed out by an atomic cursor, so rays of all producers
-//       interleave in a tile; each row carries (ray slot, weight).  Every row arrives once on the
-//       tile's "full" mbarrier (128 arrivals = tile ready).
-//   MMA issuer (1 warp, one elected lane)  per tile: layer 1 (A from shared memory, basis folded
+//       with w > threshold go to a small per-warp queue whose entries carry their ray slot (so samples of
+//       consecutive rays share a gather); every 32 of them are gathered (lane = sample: 3 planes x 4 texels
+//       x 96 B + 3 lines, 72 products), split into bf16 hi/lo and written as one ROW of the current 128-row
+//       A tile in shared memory (K-major 8x8 core matrices).  Rows are handed out by an atomic cursor, so
+//       rays of all producers interleave in a tile; each row carries (ray slot, weight).  Every row arrives
+//       once on the tile's "full" mbarrier (128 arrivals = tile ready).
+//   MMA issuer (warp W_ISSUE, one elected lane)  per tile: layer 1 (A from shared memory, basis folded
 //       into W1, K = 80) and layer 2 (A from TMEM, K = 128) as tcgen05.mma kind::f16 M=128 N=128,
 //       three bf16 products hi*hi + hi*lo + lo*hi per K-step, fp32 accumulators in TMEM;
 //       tcgen05.commit signals the consumers and frees the A tile for the producers.
-//   consumers (4 warps, thread = tile row)  epilogue 1: tcgen05.ld acc1, bias + ReLU, re-split,
+//   consumers (the last 4 warps, thread = tile row)  epilogue 1: tcgen05.ld acc1, bias + ReLU, re-split,
 //       tcgen05.st as layer 2's A operand; epilogue 2: tcgen05.ld acc2, bias + ReLU, layer 3
 //       (131 -> 3) + sigmoid; composite: w * rgb is added to the row's ray slot as 32-bit FIXED
 //       POINT with shared-memory atomics (integer adds are associative, so results are
 //       bit-identical whatever the interleaving of rows, tiles and threads); the last contributor
-//       of a ray writes its output (white background, blend, accumulate, exposure, clamp).
+//       of a ray writes its output (white background, blend, accumulate, exposure, clamp) and, in a
+//       multi-GPU run, stores the finished pixel into every peer's gathered buffer.
 //
-// The weight operands are staged once per CTA by TMA bulk copies (cp.async.bulk -> UBLKCP).
+// render_kernel_t<true> (fields with positional encodings) inserts a layer 0 (basis_mat as its own product),
+// builds the encoded layer-1 input in TMEM 64 columns at a time and streams layer 1's weight chunks by TMA.
+// Compile-time experiments kept as switches (DESIGN.md par. 10): LRF_THREADS, LRF_CONS_WARPS, LRF_SPIN_NS,
+// LRF_STEAL.  The weight operands are staged once per CTA by TMA bulk copies (cp.async.bulk -> UBLKCP).
 #include <cstdlib>
 
 #include "lrf_device.cuh"
