@@ -68,7 +68,7 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_render_sharded_equals_unsharded(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
