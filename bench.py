@@ -608,7 +608,7 @@ def main():
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": bytes_total / (args.steps * n_kern),
-                    "launches_per_step": n_kern, "peak_source": peak_src, "kernel": "lrf::render_kernel",
+                    "launches_per_step": n_kern, "peak_source": peak_src, "kernel": "lrf::render_kernel_t<false>",
                     "bytes_per_ray": bytes_total / rays_total,
                     "density_samples_per_ray": st[0] / rays_total,
                     "app_samples_per_ray": st[1] / rays_total,
