@@ -506,7 +506,7 @@ class LocalTensorfs(torch.nn.Module):
         lib = _lib.lib()
         o = plan.out_struct
         o.pix = o.rgb = o.depth = None
-        o.n_peers = 0
+        o.n_peers, o.signal_seq, o.wait_seq, o.mc_pix = 0, 0, 0, None   # (exchange fields are set for the last launch only)
         if pix is not None:
             o.pix = pix.data_ptr()
         else:
