@@ -465,6 +465,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--grid", type=int, default=None)
+    ap.add_argument("--grid-storage", default="fp32", choices=["fp32", "bf16"],
+                    help="storage type the eval kernels gather the plane / line grids from (LocalTensorfs."
+                         "set_grid_storage): fp32 = the parameters (the headline, the reference's precision); "
+                         "bf16 = bfloat16 copies, half the gather bytes (a separate, labelled line -- it renders "
+                         "the bf16-rounded field)")
     args = ap.parse_args()
     quiet_stdout()
     if args.steps is None:
@@ -491,6 +496,9 @@ def main():
 
     wl = Workload(args.workload, args.grid)
     lt = wl.build(L.LocalTensorfs, quiet=True).to(dev)
+    bf16 = args.grid_storage == "bf16"
+    if bf16:
+        lt.set_grid_storage("bf16")
     kw = wl.call_kwargs(lt, dev)
     ids_host, views_host = wl.batches()
     n_batches = ids_host.shape[0]
@@ -601,14 +609,17 @@ def main():
     roofline = None
     if world == 1:
         rays_total = BATCH * args.steps
-        bytes_total = st[0] * 576 + st[1] * 1728 + rays_total * 40
+        # "with 16-bit grid storage halve the 576 / 1728 terms and say so"
+        bytes_total = st[0] * (288 if bf16 else 576) + st[1] * (864 if bf16 else 1728) + rays_total * 40
         achieved = bytes_total / (sum(times_ms) * 1e-3) / 1e9
-        traffic, traffic_src = traffic_for(wl.name)
+        traffic, traffic_src = traffic_for(wl.name) if not bf16 else (None, None)   # (the captures are of the fp32 kernel)
         n_kern = max(launches) if launches else 1
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": bytes_total / (args.steps * n_kern),
-                    "launches_per_step": n_kern, "peak_source": peak_src, "kernel": "lrf::render_kernel_t<false>",
+                    "launches_per_step": n_kern, "peak_source": peak_src,
+                    "kernel": "lrf::render_kernel_t<false, true>" if bf16 else "lrf::render_kernel_t<false, false>",
+                    "bytes_per_sample": {"density": 288 if bf16 else 576, "appearance": 864 if bf16 else 1728},
                     "bytes_per_ray": bytes_total / rays_total,
                     "density_samples_per_ray": st[0] / rays_total,
                     "app_samples_per_ray": st[1] / rays_total,
@@ -709,10 +720,14 @@ def main():
         "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak" if scaling == "weak" else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "dtype_note": "fp32 storage and arithmetic; the two dense MLP layers run on tcgen05 as three bf16 "
+        "dtype_note": ("fp32 storage and arithmetic" if not bf16 else
+                       "NOT the headline: fp32 arithmetic on bfloat16 GRID STORAGE (--grid-storage bf16; the render "
+                       "equals the fp32 render of the bf16-rounded field, tests/test_gpu_bf16.py)") +
+                      "; the two dense MLP layers run on tcgen05 as three bf16 "
                       "products of hi/lo-split fp32 operands with fp32 TMEM accumulators (1e-7 of fp32 on rgb, "
                       "tests/test_gpu_parity.py::test_tensor_core_mlp_vs_torch_fp32)",
         "config": {"workload": wl.describe(), "workload_key": wl.name, "rays_per_batch": BATCH,
+                   "grid_storage": args.grid_storage,
                    "rays_per_step_global": rays_per_step_global,
                    "l2": "2 x 256 MiB writes between timed steps",
                    "sharding": {"weak": "every rank its own 4096-ray batch per step",

@@ -18,7 +18,8 @@
  * would add.  Plain pointers and sizes only -- no torch types.
  *
  * All pointers are DEVICE pointers on the current CUDA device unless stated otherwise; all
- * floating-point data is fp32; work is enqueued on `stream` and never synchronises the host.
+ * floating-point data is fp32 (the plane / line grids optionally bfloat16, LrfField.grid_dtype); work is
+ * enqueued on `stream` and never synchronises the host.
  * Every function returns LRF_OK (0) or a negative error code; lrf_last_error() gives the text.
  *
  * HBM layout of a field ("channel-last", one texel's components contiguous):
@@ -76,7 +77,17 @@ typedef struct LrfField {
   const float *z_vals;        /* [n_samples] per-batch distance table (tensorBase.py:419-437);
                                  the host builds it (it owns the RNG of the train-mode jitter) */
   int32_t n_samples;          /* S = 2*(nSamples/6) */
+  int32_t grid_dtype;         /* storage type of the twelve plane / line tensors: LRF_GRID_F32 (0, default) or
+                                 LRF_GRID_BF16: the dplane/dline/aplane/aline pointers then address bfloat16
+                                 data in the SAME [H][W][C] / [L][C] layout (a density texel = one 16-byte
+                                 load, an appearance texel three); arithmetic stays fp32 and the conversion
+                                 is exact, so a field whose parameters are bf16-representable renders the same
+                                 values from either storage.  Inference only: accepted by lrf_render (pe = 0),
+                                 lrf_density_feature and lrf_app_feature; every other entry point returns
+                                 LRF_ERR_UNSUPPORTED.  lrf_pack_bf16() makes the 16-bit copy. */
 } LrfField;
+#define LRF_GRID_F32 0
+#define LRF_GRID_BF16 1
 
 /* One ray batch.  Either explicit rays (TensorBase.forward's rays_chunk) or ray ids + cameras
  * (LocalTensorfs.forward; the kernel then generates origin/direction itself).
@@ -271,6 +282,10 @@ int lrf_sample_ray(const float *rays, const float *jitter, int64_t N, int32_t S,
 int lrf_frame_to_u8(const float *rgb, int32_t rgb_stride, const float *depth, int32_t depth_stride, int64_t N,
                     float d_lo, float d_hi, const unsigned char *lut, unsigned char *rgb8, unsigned char *depth8,
                     lrf_stream_t stream);
+
+/* fp32 -> bfloat16 (round to nearest even), n elements: the 16-bit copy of a channel-last plane / line
+ * tensor for LrfField.grid_dtype = LRF_GRID_BF16.  dst must be 16-byte aligned when used as a grid. */
+int lrf_pack_bf16(const float *src, void *dst, int64_t n, lrf_stream_t stream);
 
 /* [C][H][W] (contiguous NCHW parameter of the reference) -> [H][W][C] */
 int lrf_repack_nchw_to_nhwc(const float *src, float *dst, int32_t C, int32_t H, int32_t W,

@@ -36,7 +36,11 @@ class LrfField(C.Structure):
         ("act", C.c_int32),
         ("z_vals", _vp),
         ("n_samples", C.c_int32),
+        ("grid_dtype", C.c_int32),       # GRID_F32 / GRID_BF16
     ]
+
+
+GRID_F32, GRID_BF16 = 0, 1
 
 
 class LrfBatch(C.Structure):
@@ -78,7 +82,7 @@ EXPORTS = ["lrf_version", "lrf_sizeof", "lrf_last_error", "lrf_prepared_bytes", 
            "lrf_launch_info", "lrf_prepared_backward_bytes", "lrf_backward_scratch_bytes",
            "lrf_field_prepare_backward", "lrf_render_backward", "lrf_peer_barrier", "lrf_peer_signal_wait",
            "lrf_alpha_mask_build", "lrf_upsample", "lrf_density_l1", "lrf_density_l1_backward", "lrf_tv_sums",
-           "lrf_tv_sums_backward", "lrf_sample_ray", "lrf_frame_to_u8"]
+           "lrf_tv_sums_backward", "lrf_sample_ray", "lrf_frame_to_u8", "lrf_pack_bf16"]
 
 
 def _stale():
@@ -108,7 +112,7 @@ def build(force=False, verbose=False):
 _lib = None
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 def lib():
@@ -149,6 +153,7 @@ def lib():
     for name in ("lrf_density_feature_backward", "lrf_app_products_backward"):
         getattr(L, name).argtypes = [C.POINTER(LrfField), _vp, _vp, C.c_int64, _vp * 3, _vp * 3, _vp, _vp]
     L.lrf_repack_nchw_to_nhwc.argtypes = [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]
+    L.lrf_pack_bf16.argtypes = [_vp, _vp, C.c_int64, _vp]
     L.lrf_launch_info.argtypes = [C.POINTER(C.c_int32)] * 3
     L.lrf_prepared_backward_bytes.restype = C.c_size_t
     L.lrf_backward_scratch_bytes.restype = C.c_size_t

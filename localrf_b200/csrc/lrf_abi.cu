@@ -26,6 +26,7 @@ cudaError_t launch_density_feature(const FieldDev& F, const float* xyz, long lon
 cudaError_t launch_app_feature(const FieldDev& F, const float* basis, const float* xyz,
                                long long M, float* out, cudaStream_t stream);
 cudaError_t launch_repack(const float* src, float* dst, int C, long long HW, cudaStream_t stream);
+cudaError_t launch_pack_bf16(const float* src, void* dst, long long n, int n_sms, cudaStream_t stream);
 cudaError_t launch_alpha_mask_build(const FieldDev& F, const float* aabb_max, const int* dims, float length,
                                     float thres, float* alpha_scratch, float* mask,
                                     unsigned long long* kept, int n_sms, cudaStream_t stream);
@@ -114,8 +115,14 @@ int device_info(DevInfo& d) {
 
 // validates the parts of a field every entry point needs and fills the device-side view
 int make_field(const LrfField* f, bool need_mlp, bool need_table, const void* prepared,
-               lrf::FieldDev& F, bool allow_pe = false) {
+               lrf::FieldDev& F, bool allow_pe = false, bool allow_bf16 = false) {
   if (!f) return fail(LRF_ERR_INVALID, "field is NULL");
+  if (f->grid_dtype != LRF_GRID_F32 && f->grid_dtype != LRF_GRID_BF16)
+    return fail(LRF_ERR_INVALID, "grid_dtype must be LRF_GRID_F32 or LRF_GRID_BF16");
+  if (f->grid_dtype == LRF_GRID_BF16 && !allow_bf16)
+    return fail(LRF_ERR_UNSUPPORTED, "bf16 grid storage is built for lrf_render (pe = 0), lrf_density_feature and "
+                                     "lrf_app_feature only (inference); pass the fp32 parameters here");
+  F.grid16 = f->grid_dtype == LRF_GRID_BF16 ? 1 : 0;
   if (f->n_dcomp != lrf::CD || f->n_acomp != lrf::CA)
     return fail(LRF_ERR_UNSUPPORTED, "only density_n_comp=8 / appearance_n_comp=24 per plane are built");
   for (int a = 0; a < 3; ++a) {
@@ -177,7 +184,7 @@ int make_field(const LrfField* f, bool need_mlp, bool need_table, const void* pr
 
 extern "C" {
 
-int lrf_version(void) { return 2; }
+int lrf_version(void) { return 3; }
 
 size_t lrf_sizeof(int32_t which) {
   switch (which) {
@@ -226,10 +233,12 @@ int lrf_render(const LrfField* f, const void* prepared, const LrfBatch* b, const
   if (!b || !o) return fail(LRF_ERR_INVALID, "batch or outputs is NULL");
   if (!prepared) return fail(LRF_ERR_INVALID, "prepared is NULL (call lrf_field_prepare first)");
   lrf::FieldDev F;
-  int rc = make_field(f, true, true, prepared, F, /*allow_pe=*/true);
+  int rc = make_field(f, true, true, prepared, F, /*allow_pe=*/true, /*allow_bf16=*/true);
   if (rc != LRF_OK) return rc;
   if ((F.fea_pe || F.view_pe) && (!f->w3 || ((uintptr_t)prepared & 1023)))
     return fail(LRF_ERR_INVALID, "positional encodings need w3 and a 1024-byte aligned prepared block");
+  if ((F.fea_pe || F.view_pe) && F.grid16)
+    return fail(LRF_ERR_UNSUPPORTED, "bf16 grid storage is built for fields without positional encodings");
   if (b->n_rays < 0) return fail(LRF_ERR_INVALID, "n_rays < 0");
   if (b->n_rays == 0) {
     // nothing to render; a rank with an empty shard must still publish its step to the peers
@@ -337,7 +346,7 @@ int lrf_mlp_forward(const void* prepared, const float* feats, const float* viewd
 int lrf_density_feature(const LrfField* f, const float* xyz, int64_t M, float* out,
                         lrf_stream_t stream) {
   lrf::FieldDev F;
-  int rc = make_field(f, false, false, nullptr, F);
+  int rc = make_field(f, false, false, nullptr, F, false, /*allow_bf16=*/true);
   if (rc != LRF_OK) return rc;
   if (M < 0 || (M > 0 && (!xyz || !out))) return fail(LRF_ERR_INVALID, "bad xyz/out/M");
   cudaError_t e = lrf::launch_density_feature(F, xyz, M, out, (cudaStream_t)stream);
@@ -348,7 +357,7 @@ int lrf_density_feature(const LrfField* f, const float* xyz, int64_t M, float* o
 int lrf_app_feature(const LrfField* f, const float* xyz, int64_t M, float* out,
                     lrf_stream_t stream) {
   lrf::FieldDev F;
-  int rc = make_field(f, false, false, nullptr, F);
+  int rc = make_field(f, false, false, nullptr, F, false, /*allow_bf16=*/true);
   if (rc != LRF_OK) return rc;
   if (f->app_dim != lrf::APP_DIM) return fail(LRF_ERR_UNSUPPORTED, "only app_dim=27 is built");
   if (!f->basis) return fail(LRF_ERR_INVALID, "basis is NULL");
@@ -581,6 +590,17 @@ int lrf_peer_signal_wait(unsigned long long* const* peer_flags, int32_t rank, in
       return fail(LRF_ERR_INVALID, "peer flag arrays must be non-NULL and 8-byte aligned");
   cudaError_t e = lrf::launch_peer_barrier(peer_flags, rank, world, seq, wait_seq, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "peer_barrier_kernel");
+  return LRF_OK;
+}
+
+int lrf_pack_bf16(const float* src, void* dst, int64_t n, lrf_stream_t stream) {
+  if (n < 0 || (n > 0 && (!src || !dst))) return fail(LRF_ERR_INVALID, "bad src/dst/n");
+  if ((uintptr_t)dst & 1) return fail(LRF_ERR_INVALID, "dst must be 2-byte aligned");
+  DevInfo d;
+  int rc = device_info(d);
+  if (rc != LRF_OK) return rc;
+  cudaError_t e = lrf::launch_pack_bf16(src, dst, n, d.n_sms, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "pack_bf16_kernel");
   return LRF_OK;
 }
 

@@ -275,15 +275,17 @@ __global__ void prepare_pe_kernel(const float* __restrict__ basis, const float* 
   for (int e = t; e < 4; e += stride) tail[TAIL_B3 + e] = e < 3 ? b3[e] : 0.0f;
 }
 
+template <bool H16>      // H16: bf16 grid storage (LrfField.grid_dtype)
 __global__ void density_feature_kernel(const FieldDev F, const float* __restrict__ xyz,
                                        long long M, float* __restrict__ out) {
   long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float q[3] = {xyz[3 * m], xyz[3 * m + 1], xyz[3 * m + 2]};
-  out[m] = density_feature(F, q);
+  out[m] = density_feature_t<H16>(F, q);
 }
 
 // compute_appfeature: 72 products then basis_mat (unfolded: this entry returns the 27-vector)
+template <bool H16>
 __global__ void app_feature_kernel(const FieldDev F, const float* __restrict__ basis,
                                    const float* __restrict__ xyz, long long M,
                                    float* __restrict__ out) {
@@ -291,9 +293,9 @@ __global__ void app_feature_kernel(const FieldDev F, const float* __restrict__ b
   if (m >= M) return;
   float q[3] = {xyz[3 * m], xyz[3 * m + 1], xyz[3 * m + 2]};
   float feat[NF];
-  app_plane_features(F, 0, q, feat);
-  app_plane_features(F, 1, q, feat + CA);
-  app_plane_features(F, 2, q, feat + 2 * CA);
+  app_plane_features_t<H16>(F, 0, q, feat);
+  app_plane_features_t<H16>(F, 1, q, feat + CA);
+  app_plane_features_t<H16>(F, 2, q, feat + 2 * CA);
   for (int o = 0; o < APP_DIM; ++o) {
     float s = 0.0f;
 #pragma unroll
@@ -349,14 +351,16 @@ cudaError_t launch_prepare_pe(const float* basis, const float* w1, const float* 
 cudaError_t launch_density_feature(const FieldDev& F, const float* xyz, long long M, float* out,
                                    cudaStream_t stream) {
   if (M == 0) return cudaSuccess;
-  density_feature_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(F, xyz, M, out);
+  if (F.grid16) density_feature_kernel<true><<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(F, xyz, M, out);
+  else density_feature_kernel<false><<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(F, xyz, M, out);
   return cudaGetLastError();
 }
 
 cudaError_t launch_app_feature(const FieldDev& F, const float* basis, const float* xyz, long long M,
                                float* out, cudaStream_t stream) {
   if (M == 0) return cudaSuccess;
-  app_feature_kernel<<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(F, basis, xyz, M, out);
+  if (F.grid16) app_feature_kernel<true><<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(F, basis, xyz, M, out);
+  else app_feature_kernel<false><<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(F, basis, xyz, M, out);
   return cudaGetLastError();
 }
 
@@ -364,6 +368,22 @@ cudaError_t launch_repack(const float* src, float* dst, int C, long long HW, cud
   long long n = HW * C;
   if (n == 0) return cudaSuccess;
   repack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, C, HW);
+  return cudaGetLastError();
+}
+
+// fp32 -> bfloat16, round to nearest even (lrf_pack_bf16): the 16-bit copy of a plane / line tensor
+__global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
+    dst[e] = __float2bfloat16_rn(src[e]);
+}
+
+cudaError_t launch_pack_bf16(const float* src, void* dst, long long n, int n_sms, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)n_sms * 8;
+  pack_bf16_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n);
   return cudaGetLastError();
 }
 

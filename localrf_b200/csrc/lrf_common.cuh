@@ -83,6 +83,7 @@ struct FieldDev {
   int S;
   int fea_pe, view_pe;        // positional encodings of the MLP (tensorBase.py:14-21,115-125); 0, 0 = the folded fast path
   const float* w3;            // mlp_view[0].weight [3][128 + 3 (1 + 2 view_pe)] (the producers' view term)
+  int grid16;                 // 1: the twelve plane / line pointers address bfloat16 texels (LrfField.grid_dtype)
 };
 
 struct BatchDev {

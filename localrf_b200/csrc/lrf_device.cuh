@@ -374,6 +374,96 @@ __device__ __forceinline__ void app_plane_features(const FieldDev& F, int i, con
   }
 }
 
+// ---- 16-bit grid storage (LrfField.grid_dtype = LRF_GRID_BF16) ----------------------------------
+// The same gathers reading bfloat16 texels in the same [H][W][C] / [L][C] layout: a density texel is ONE
+// 16-byte load (8 components), an appearance texel three (24 components) -- half the sectors and half the
+// load instructions of the fp32 grids.  bf16 -> fp32 is exact (a 16-bit shift) and the arithmetic is the fp32
+// code's, expression for expression, so a field whose parameters are bf16-representable renders the same
+// values from either storage.
+struct Tex8 { float v[8]; };
+__device__ __forceinline__ Tex8 ldg8_bf16(const __nv_bfloat16* p) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  Tex8 t;
+  t.v[0] = __uint_as_float(r.x << 16); t.v[1] = __uint_as_float(r.x & 0xffff0000u);
+  t.v[2] = __uint_as_float(r.y << 16); t.v[3] = __uint_as_float(r.y & 0xffff0000u);
+  t.v[4] = __uint_as_float(r.z << 16); t.v[5] = __uint_as_float(r.z & 0xffff0000u);
+  t.v[6] = __uint_as_float(r.w << 16); t.v[7] = __uint_as_float(r.w & 0xffff0000u);
+  return t;
+}
+
+// compute_densityfeature for one point, bf16 texels (cf. density_feature)
+__device__ __forceinline__ float density_feature_bf16(const FieldDev& F, const float* q) {
+  static_assert(CD == 8, "one 16-byte load per density texel");
+  float sigma = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int W = F.g[mat0(i)], H = F.g[mat1(i)], L = F.g[vecm(i)];
+    int x0, x1, y0, y1, l0, l1;
+    float tx, ty, tl;
+    grid_coord(q[mat0(i)], W, x0, x1, tx);
+    grid_coord(q[mat1(i)], H, y0, y1, ty);
+    grid_coord(q[vecm(i)], L, l0, l1, tl);
+    const __nv_bfloat16* P = reinterpret_cast<const __nv_bfloat16*>(F.dplane[i]);
+    const __nv_bfloat16* Ln = reinterpret_cast<const __nv_bfloat16*>(F.dline[i]);
+    const Tex8 a = ldg8_bf16(P + ((size_t)y0 * W + x0) * CD), b = ldg8_bf16(P + ((size_t)y0 * W + x1) * CD);
+    const Tex8 c = ldg8_bf16(P + ((size_t)y1 * W + x0) * CD), d = ldg8_bf16(P + ((size_t)y1 * W + x1) * CD);
+    const Tex8 u = ldg8_bf16(Ln + (size_t)l0 * CD), v = ldg8_bf16(Ln + (size_t)l1 * CD);
+    float w00 = (1.0f - tx) * (1.0f - ty), w01 = tx * (1.0f - ty);
+    float w10 = (1.0f - tx) * ty, w11 = tx * ty;
+    float s = 0.0f;
+#pragma unroll
+    for (int e = 0; e < CD; ++e) {
+      float px = a.v[e] * w00 + b.v[e] * w01 + c.v[e] * w10 + d.v[e] * w11;
+      s += px * (u.v[e] * (1.0f - tl) + v.v[e] * tl);
+    }
+    sigma += s;
+  }
+  return sigma;
+}
+
+// one plane's 24 appearance features of one point, bf16 texels (cf. app_plane_features)
+__device__ __forceinline__ void app_plane_features_bf16(const FieldDev& F, int i, const float* q,
+                                                        float* out /*[CA]*/) {
+  static_assert(CA % 8 == 0, "16-byte loads of 8 components");
+  const int W = F.g[mat0(i)], H = F.g[mat1(i)], L = F.g[vecm(i)];
+  int x0, x1, y0, y1, l0, l1;
+  float tx, ty, tl;
+  grid_coord(q[mat0(i)], W, x0, x1, tx);
+  grid_coord(q[mat1(i)], H, y0, y1, ty);
+  grid_coord(q[vecm(i)], L, l0, l1, tl);
+  const __nv_bfloat16* P = reinterpret_cast<const __nv_bfloat16*>(F.aplane[i]);
+  const __nv_bfloat16* p00 = P + ((size_t)y0 * W + x0) * CA;
+  const __nv_bfloat16* p01 = P + ((size_t)y0 * W + x1) * CA;
+  const __nv_bfloat16* p10 = P + ((size_t)y1 * W + x0) * CA;
+  const __nv_bfloat16* p11 = P + ((size_t)y1 * W + x1) * CA;
+  const __nv_bfloat16* q0 = reinterpret_cast<const __nv_bfloat16*>(F.aline[i]) + (size_t)l0 * CA;
+  const __nv_bfloat16* q1 = reinterpret_cast<const __nv_bfloat16*>(F.aline[i]) + (size_t)l1 * CA;
+  float w00 = (1.0f - tx) * (1.0f - ty), w01 = tx * (1.0f - ty);
+  float w10 = (1.0f - tx) * ty, w11 = tx * ty;
+#pragma unroll
+  for (int c8 = 0; c8 < CA / 8; ++c8) {
+    const Tex8 a = ldg8_bf16(p00 + 8 * c8), b = ldg8_bf16(p01 + 8 * c8), c = ldg8_bf16(p10 + 8 * c8),
+               d = ldg8_bf16(p11 + 8 * c8);
+    const Tex8 u = ldg8_bf16(q0 + 8 * c8), v = ldg8_bf16(q1 + 8 * c8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      out[8 * c8 + e] = (a.v[e] * w00 + b.v[e] * w01 + c.v[e] * w10 + d.v[e] * w11) *
+                        (u.v[e] * (1.0f - tl) + v.v[e] * tl);
+  }
+}
+
+// storage-type dispatch (compile time): H16 = bf16 texels
+template <bool H16>
+__device__ __forceinline__ float density_feature_t(const FieldDev& F, const float* q) {
+  if constexpr (H16) return density_feature_bf16(F, q);
+  else return density_feature(F, q);
+}
+template <bool H16>
+__device__ __forceinline__ void app_plane_features_t(const FieldDev& F, int i, const float* q, float* out) {
+  if constexpr (H16) app_plane_features_bf16(F, i, q, out);
+  else app_plane_features(F, i, q, out);
+}
+
 // ---- warp primitives ----------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

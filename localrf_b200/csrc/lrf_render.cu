@@ -229,6 +229,41 @@ __device__ __forceinline__ void app_row(const FieldDev& F, const float* q, unsig
   }
 }
 
+// the same row from bf16 texels (LrfField.grid_dtype = LRF_GRID_BF16): three 16-byte loads per texel
+__device__ __forceinline__ void app_row_bf16(const FieldDev& F, const float* q, unsigned char* a_hi,
+                                             unsigned char* a_lo, int row) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int W = F.g[mat0(i)], H = F.g[mat1(i)], L = F.g[vecm(i)];
+    int x0, x1, y0, y1, l0, l1;
+    float tx, ty, tl;
+    grid_coord(q[mat0(i)], W, x0, x1, tx);
+    grid_coord(q[mat1(i)], H, y0, y1, ty);
+    grid_coord(q[vecm(i)], L, l0, l1, tl);
+    const __nv_bfloat16* P = reinterpret_cast<const __nv_bfloat16*>(F.aplane[i]);
+    const __nv_bfloat16* p00 = P + ((size_t)y0 * W + x0) * CA;
+    const __nv_bfloat16* p01 = P + ((size_t)y0 * W + x1) * CA;
+    const __nv_bfloat16* p10 = P + ((size_t)y1 * W + x0) * CA;
+    const __nv_bfloat16* p11 = P + ((size_t)y1 * W + x1) * CA;
+    const __nv_bfloat16* q0 = reinterpret_cast<const __nv_bfloat16*>(F.aline[i]) + (size_t)l0 * CA;
+    const __nv_bfloat16* q1 = reinterpret_cast<const __nv_bfloat16*>(F.aline[i]) + (size_t)l1 * CA;
+    const float w00 = (1.0f - tx) * (1.0f - ty), w01 = tx * (1.0f - ty);
+    const float w10 = (1.0f - tx) * ty, w11 = tx * ty;
+    const float u0 = 1.0f - tl;
+#pragma unroll
+    for (int c8 = 0; c8 < CA / 8; ++c8) {
+      const Tex8 a = ldg8_bf16(p00 + 8 * c8), b = ldg8_bf16(p01 + 8 * c8), c = ldg8_bf16(p10 + 8 * c8),
+                 d = ldg8_bf16(p11 + 8 * c8);
+      const Tex8 u = ldg8_bf16(q0 + 8 * c8), w = ldg8_bf16(q1 + 8 * c8);
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        v[e] = (a.v[e] * w00 + b.v[e] * w01 + c.v[e] * w10 + d.v[e] * w11) * (u.v[e] * u0 + w.v[e] * tl);
+      store_chunk(a_hi, a_lo, row, i * (CA / 8) + c8, K1_CHUNKS, v);
+    }
+  }
+}
+
 struct ProdCtx {
   unsigned char* smem;
   const SmemV3* L;
@@ -292,6 +327,7 @@ struct WarpQ {
 
 // gathers the first n (<= 32) queued samples (each with its own ray, read from its slot) and submits
 // them as tile rows.  Their slots' `pending` counts were raised when the samples were selected.
+template <bool H16>
 __device__ __forceinline__ void flush_rows(const ProdCtx& P, const FieldDev& F, const float* z_s,
                                            const Slot* slots, const WarpQ& Q, int n) {
   unsigned int start = 0;
@@ -309,7 +345,8 @@ __device__ __forceinline__ void flush_rows(const ProdCtx& P, const FieldDev& F, 
     sample_pos(F, R, z_s[k], p, q);
     wait_tile_free(P.ctrl, T);
     unsigned char* a_hi = P.smem + P.L->a1 + b * (2 * OPER1_BYTES);
-    app_row(F, q, a_hi, a_hi + OPER1_BYTES, row);
+    if constexpr (H16) app_row_bf16(F, q, a_hi, a_hi + OPER1_BYTES, row);
+    else app_row(F, q, a_hi, a_hi + OPER1_BYTES, row);
     P.smem[P.L->mslot + b * TM + row] = (unsigned char)sid;
     reinterpret_cast<float*>(P.smem + P.L->mw)[b * TM + row] = Q.qw[P.lane];
     fence_async_smem();                  // generic-proxy writes -> visible to the tensor core
@@ -320,6 +357,7 @@ __device__ __forceinline__ void flush_rows(const ProdCtx& P, const FieldDev& F, 
 
 // appends the lanes with on == true (mask m = their ballot) to the warp's queue; flushes 32 rows when it
 // holds >= 32.  The caller has already added popc(m) to the slot's pending count.
+template <bool H16>
 __device__ __forceinline__ void queue_push(const ProdCtx& P, const FieldDev& F, const float* z_s,
                                            const Slot* slots, WarpQ& Q, unsigned m, bool on, int k,
                                            float wgt, int slot_id) {
@@ -332,7 +370,7 @@ __device__ __forceinline__ void queue_push(const ProdCtx& P, const FieldDev& F, 
   Q.n_app += __popc(m);
   __syncwarp();
   if (Q.qn >= 32) {
-    flush_rows(P, F, z_s, slots, Q, 32);
+    flush_rows<H16>(P, F, z_s, slots, Q, 32);
     unsigned short tk = 0; float tw = 0.0f; unsigned char ts = 0;
     if (lane < Q.qn - 32) { tk = Q.qk[32 + lane]; tw = Q.qw[32 + lane]; ts = Q.qs[32 + lane]; }
     __syncwarp();
@@ -343,6 +381,7 @@ __device__ __forceinline__ void queue_push(const ProdCtx& P, const FieldDev& F, 
 }
 
 // alpha of sample k of the ray in slot-resident form (tensorBase.py:581-610); counts valid samples
+template <bool H16>
 __device__ __forceinline__ float sample_alpha(const FieldDev& F, const RaySm& R, const float* z_s, int k,
                                               int S, int& marched) {
   const float z = z_s[k];
@@ -352,7 +391,7 @@ __device__ __forceinline__ float sample_alpha(const FieldDev& F, const RaySm& R,
   if (valid && F.alpha_vol) valid = alpha_mask(F, p) > 0.0f;  // tensorBase.py:593-598
   float sigma = 0.0f;
   if (valid) {
-    sigma = feature2density(density_feature(F, q), F.density_shift, F.act);
+    sigma = feature2density(density_feature_t<H16>(F, q), F.density_shift, F.act);
     ++marched;
   }
   const float dist = z_s[k + 1] - z;
@@ -362,6 +401,7 @@ __device__ __forceinline__ float sample_alpha(const FieldDev& F, const RaySm& R,
 }
 
 // One claimed step (32 samples) of the ray described by `rec`: see RayRec.
+template <bool H16>
 __device__ __forceinline__ void process_step(const ProdCtx& P, const FieldDev& F, const BatchDev& B,
                                              const float* z_s, Slot* slots, RayRec* rec, int s, WarpQ& Q) {
   const int lane = P.lane, S = F.S, k = s * 32 + lane;
@@ -374,7 +414,7 @@ __device__ __forceinline__ void process_step(const ProdCtx& P, const FieldDev& F
   const bool skip = (unsigned)s >= *reinterpret_cast<volatile unsigned int*>(&rec->stop_at);
   float alpha = 0.0f;
   int marched = 0;
-  if (!skip && k < S) alpha = sample_alpha(F, R, z_s, k, S, marched);
+  if (!skip && k < S) alpha = sample_alpha<H16>(F, R, z_s, k, S, marched);
   const float f = (k < S) ? (1.0f - alpha) + 1e-10f : 1.0f;
   const float inc = warp_scan_mul(f, lane);
   float exc = __shfl_up_sync(0xffffffffu, inc, 1);
@@ -409,14 +449,16 @@ __device__ __forceinline__ void process_step(const ProdCtx& P, const FieldDev& F
     __threadfence_block();
     atomicOr(&rec->done, 1u << s);
   }
-  queue_push(P, F, z_s, slots, Q, m, on, k, wgt, slot_id);
+  queue_push<H16>(P, F, z_s, slots, Q, m, on, k, wgt, slot_id);
 }
 
 // =================================================================================================
 // PE = the field has positional encodings (fea_pe > 0 or view_pe > 0): basis_mat is its own tensor-core
 // product (layer 0), the consumers build the encoded layer-1 input chunk by chunk in TMEM, layer 1's weight
 // operand is streamed by TMA in K-chunks of 64.  PE = false is the reference-default fast path (folded basis).
-template <bool PE>
+// H16 = the grids are stored as bfloat16 (LrfField.grid_dtype): the gathers of the producers read 16-byte
+// texel pieces of 8 components; everything downstream of the gathers is the same code.
+template <bool PE, bool H16 = false>
 __global__ void __launch_bounds__(THREADS, 1)
 render_kernel_t(const FieldDev F, const BatchDev B, const int nprod) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -515,7 +557,7 @@ render_kernel_t(const FieldDev F, const BatchDev B, const int nprod) {
         st = __shfl_sync(0xffffffffu, st, 0);
         if (st == 0) break;
         if (spins == SPIN_PAD) {
-          if (Q.qn > 0) { flush_rows(P, F, z_s, slots, Q, Q.qn); Q.qn = 0; }
+          if (Q.qn > 0) { flush_rows<H16>(P, F, z_s, slots, Q, Q.qn); Q.qn = 0; }
           pad_open_tile(P);
           spins = 0;
         }
@@ -586,7 +628,7 @@ render_kernel_t(const FieldDev F, const BatchDev B, const int nprod) {
             if (lane == 0) { __threadfence_block(); atomicOr(&rec->ready, mask); atomicOr(&rec->done, mask); }
             break;
           }
-          process_step(P, F, B, z_s, slots, rec, (int)st, Q);
+          process_step<H16>(P, F, B, z_s, slots, rec, (int)st, Q);
         }
         while (*reinterpret_cast<volatile unsigned int*>(&rec->done) != full_mask) { }   // helpers' steps
         __threadfence_block();
@@ -601,7 +643,7 @@ render_kernel_t(const FieldDev F, const BatchDev B, const int nprod) {
         for (; k0 < S; k0 += 32) {
           const int k = k0 + lane;
           float alpha = 0.0f;
-          if (k < S) alpha = sample_alpha(F, R, z_s, k, S, marched);
+          if (k < S) alpha = sample_alpha<H16>(F, R, z_s, k, S, marched);
           const float f = (k < S) ? (1.0f - alpha) + 1e-10f : 1.0f;
           const float inc = warp_scan_mul(f, lane);
           float exc = __shfl_up_sync(0xffffffffu, inc, 1);
@@ -619,7 +661,7 @@ render_kernel_t(const FieldDev F, const BatchDev B, const int nprod) {
             const bool on = (k < S) && (wgt > F.weight_thres);          // tensorBase.py:622
             const unsigned m = __ballot_sync(0xffffffffu, on);
             if (lane == 0 && m) atomicAdd(&slot->pending, __popc(m));
-            queue_push(P, F, z_s, slots, Q, m, on, k, wgt, slot_id);
+            queue_push<H16>(P, F, z_s, slots, Q, m, on, k, wgt, slot_id);
             if (carry < T_EPS) { k0 += 32; break; }                      // early ray termination
           }
         }
@@ -645,7 +687,7 @@ render_kernel_t(const FieldDev F, const BatchDev B, const int nprod) {
             const bool on = (k < S) && (wgt > F.weight_thres);
             const unsigned m = __ballot_sync(0xffffffffu, on);
             if (lane == 0 && m) atomicAdd(&slot->pending, __popc(m));
-            queue_push(P, F, z_s, slots, Q, m, on, k, wgt, slot_id);
+            queue_push<H16>(P, F, z_s, slots, Q, m, on, k, wgt, slot_id);
           }
         }
         n_march += (unsigned long long)warp_sum((float)marched);
@@ -677,7 +719,7 @@ render_kernel_t(const FieldDev F, const BatchDev B, const int nprod) {
             st = __shfl_sync(0xffffffffu, st, 0);
             if (st >= (unsigned)n_steps) break;
             __threadfence_block();
-            process_step(P, F, B, z_s, slots, other, (int)st, Q);
+            process_step<H16>(P, F, B, z_s, slots, other, (int)st, Q);
             any = true;
           }
         }
@@ -687,7 +729,7 @@ render_kernel_t(const FieldDev F, const BatchDev B, const int nprod) {
         }
       }
     }
-    if (Q.qn > 0) { flush_rows(P, F, z_s, slots, Q, Q.qn); Q.qn = 0; }
+    if (Q.qn > 0) { flush_rows<H16>(P, F, z_s, slots, Q, Q.qn); Q.qn = 0; }
     // -- the last producer completes the open tile and publishes the tile count ----------------------
     if (lane == 0 && B.stats) { atomicAdd(B.stats, n_march); atomicAdd(B.stats + 1, Q.n_app); }
     unsigned int d = 0;
@@ -981,15 +1023,17 @@ cudaError_t launch_render(const FieldDev& F, const BatchDev& B, int n_sms, int m
   const int nprod = pick_nprod(F.S, floater, max_smem, pe);
   if (nprod < 1) return cudaErrorInvalidConfiguration;
   const size_t smem = (size_t)smem_v3(F.S, floater, nprod, pe).total;
-  static size_t configured[2][64] = {{0}, {0}};   // per kernel, per device: the attribute belongs to the device's context
+  const int variant = pe ? 1 : (F.grid16 ? 2 : 0);   // (bf16 grids with positional encodings are refused by the ABI)
+  static size_t configured[3][64] = {{0}, {0}, {0}};   // per kernel, per device: the attribute belongs to the device's context
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev >= 0 && dev < 64 && smem > configured[pe][dev]) {
-    e = pe ? cudaFuncSetAttribute(render_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-           : cudaFuncSetAttribute(render_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (dev >= 0 && dev < 64 && smem > configured[variant][dev]) {
+    e = variant == 1 ? cudaFuncSetAttribute(render_kernel_t<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+      : variant == 2 ? cudaFuncSetAttribute(render_kernel_t<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                     : cudaFuncSetAttribute(render_kernel_t<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[pe][dev] = smem;
+    configured[variant][dev] = smem;
   }
   e = cudaMemsetAsync(B.sched, 0, 2 * sizeof(unsigned long long), stream);   // ray counter + finished-CTA counter
   if (e != cudaSuccess) return e;
@@ -997,8 +1041,9 @@ cudaError_t launch_render(const FieldDev& F, const BatchDev& B, int n_sms, int m
   long long want = (B.n_rays + 7) / 8;
   int grid = (int)(want < n_sms ? want : n_sms);
   if (grid < 1) grid = 1;
-  if (pe) render_kernel_t<true><<<grid, THREADS, smem, stream>>>(F, B, nprod);
-  else render_kernel_t<false><<<grid, THREADS, smem, stream>>>(F, B, nprod);
+  if (variant == 1) render_kernel_t<true, false><<<grid, THREADS, smem, stream>>>(F, B, nprod);
+  else if (variant == 2) render_kernel_t<false, true><<<grid, THREADS, smem, stream>>>(F, B, nprod);
+  else render_kernel_t<false, false><<<grid, THREADS, smem, stream>>>(F, B, nprod);
   return cudaGetLastError();
 }
 

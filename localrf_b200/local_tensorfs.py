@@ -143,10 +143,21 @@ class LocalTensorfs(torch.nn.Module):
         else:
             world2rf = torch.zeros(3, device=self.device)
         self.tensorfs.append(TensorVMSplit(device=self.device, **self.tensorf_args))
+        if self.__dict__.get("grid_storage", "fp32") != "fp32":
+            self.tensorfs[-1].set_grid_storage(self.grid_storage)
         self.world2rf.append(world2rf.clone().detach())
         self.rf_iter.append(0)
         groups = self.tensorfs[-1].get_optparam_groups(self.rf_lr_init, self.rf_lr_basis)
         self.rf_optimizer = torch.optim.Adam(groups, betas=(0.9, 0.99))
+
+    def set_grid_storage(self, kind="fp32"):
+        """Inference storage type of every field's grids (TensorBase.set_grid_storage): "fp32" or "bf16"
+        (eval renders gather bfloat16 copies: half the bytes per texel; training is unaffected).  Fields
+        appended later inherit the setting."""
+        for rf in self.tensorfs:
+            rf.set_grid_storage(kind)
+        self.__dict__["grid_storage"] = kind
+        return self
 
     def append_frame(self):
         """Adds one frame's pose / exposure parameters, initialised from the previous frame

@@ -95,7 +95,7 @@ class _RenderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, z, white_bg, rays, *params):
         rays_c = rays.detach().to(torch.float32).contiguous()
-        rgb, depth = module._render_fused(rays_c, z, white_bg, 0.0, False, None)
+        rgb, depth = module._render_fused(rays_c, z, white_bg, 0.0, False, None, fp32=True)
         ctx.module, ctx.white_bg = module, white_bg
         # the backward re-reads the module's live parameters (nothing per-sample is saved): remember
         # what the forward saw, so an in-place update / upsample / mask rebuild in between raises like
@@ -133,7 +133,7 @@ class _RenderFn(torch.autograd.Function):
         d_rays = torch.empty_like(rays)
         lib = _lib.lib()
         with torch.cuda.device(dev):
-            fs, _ = m.field_and_prepared(z)
+            fs, _ = m.field_and_prepared(z, fp32=True)
             bp = m._prepared_backward()
             need = lib.lrf_backward_scratch_bytes(n, z.numel())
             scratch = m.__dict__.get("_bwd_scratch")
@@ -334,6 +334,7 @@ class TensorBase(torch.nn.Module):
         self.init_render_func(shadingMode, pos_pe, view_pe, fea_pe, featureC, device)
         self._prepared = None
         self.last_weights = None     # set by forward(..., return_weights=True)
+        self.grid_storage = "fp32"   # see set_grid_storage()
 
     # -- construction helpers ---------------------------------------------------------------------
     def init_render_func(self, shadingMode, pos_pe, view_pe, fea_pe, featureC, device):
@@ -380,8 +381,8 @@ class TensorBase(torch.nn.Module):
         if self.alphaMask is not None:
             self.alphaMask = self.alphaMask.to(device)
         self._prepared = None
-        self.__dict__.pop("_prep_memo", None)
-        self.__dict__.pop("_fs_memo", None)
+        for memo in ("_prep_memo", "_fs_memo", "_fs16_memo", "_g16_memo"):
+            self.__dict__.pop(memo, None)
         return super().to(device)
 
     # -- the per-batch distance table (tensorBase.py:419-437) -------------------------------------
@@ -422,7 +423,51 @@ class TensorBase(torch.nn.Module):
         raise ValueError(self.fea2denseAct)
 
     # -- C-ABI marshalling ------------------------------------------------------------------------
-    def _field_struct(self, z=None, need_mlp=True):
+    def set_grid_storage(self, kind="fp32"):
+        """Storage type the INFERENCE kernels read the plane / line grids from.
+
+        "fp32" (default): the parameters themselves.  "bf16": bfloat16 copies in the same channel-last
+        layout (LrfField.grid_dtype = LRF_GRID_BF16) -- a density texel is one 16-byte load, an appearance
+        texel three, i.e. half the gather bytes and half the load instructions.  The copies are made by
+        lrf_pack_bf16 (round to nearest even) and refreshed whenever a parameter changes; arithmetic stays
+        fp32, so the render equals the fp32 render of the bf16-rounded parameters (exactly so for a field
+        whose grids are bf16-representable, e.g. a checkpoint stored in bf16).  The parameters, `state_dict`
+        and everything that records autograd (training) are untouched: they keep reading fp32."""
+        if kind not in ("fp32", "bf16"):
+            raise ValueError("grid storage must be 'fp32' or 'bf16'")
+        if kind == "bf16" and (self.fea_pe or self.view_pe):
+            raise NotImplementedError("localrf_b200: bf16 grid storage is built for fields without positional encodings")
+        self.grid_storage = kind
+        if kind == "fp32":
+            self.__dict__.pop("_g16_memo", None)
+            self.__dict__.pop("_fs16_memo", None)
+        return self
+
+    def _grids16(self):
+        """bfloat16 copies of the twelve grids (memory [H][W][C] / [L][C]), rebuilt when a parameter is
+        replaced or updated in place.  -> dict name -> [3 tensors]"""
+        names = (("dplane", self.density_plane), ("dline", self.density_line),
+                 ("aplane", self.app_plane), ("aline", self.app_line))
+        src = [p for _, plist in names for p in plist]
+        key = tuple((p.data_ptr(), p._version) for p in src)
+        memo = self.__dict__.get("_g16_memo")
+        if memo is None or memo[0] != key:
+            lib = _lib.lib()
+            out = {}
+            for name, plist in names:
+                out[name] = []
+                for p in plist:
+                    dev = p.device
+                    dst = torch.empty(p.numel(), dtype=torch.bfloat16, device=dev)
+                    with torch.cuda.device(dev):
+                        _lib.check(lib.lrf_pack_bf16(_ptr(p.detach()), _ptr(dst), p.numel(), _stream(dev)))
+                    out[name].append(dst)
+            key = tuple((p.data_ptr(), p._version) for p in src)
+            memo = (key, out, src)
+            self.__dict__["_g16_memo"] = memo
+        return memo[1]
+
+    def _field_struct(self, z=None, need_mlp=True, grid16=False):
         s = _lib.LrfField()
         keep = []
         g = self._grid_host
@@ -482,6 +527,14 @@ class TensorBase(torch.nn.Module):
         if z is not None:
             s.z_vals = z.data_ptr()
             s.n_samples = z.numel()
+        if grid16:
+            # (after the loop above: the fp32 parameters are channel-last by now, so the copies are too)
+            g16 = self._grids16()
+            for name, tensors in g16.items():
+                for i, t in enumerate(tensors):
+                    getattr(s, name)[i] = t.data_ptr()
+            s.grid_dtype = _lib.GRID_BF16
+            keep.append(g16)
         return s, keep
 
     def _host_copy(self, slot, param):
@@ -496,11 +549,13 @@ class TensorBase(torch.nn.Module):
             self.__dict__[slot] = cached
         return cached[1]
 
-    def field_and_prepared(self, z):
+    def field_and_prepared(self, z, fp32=False):
         """(LrfField struct, prepared block) for this field, memoised: the ctypes struct is rebuilt
         only when a tensor it points at is replaced, the prepared block only when the MLP / basis
         weights change (data pointer or version counter) -- every optimiser step while training,
-        never inside an eval loop."""
+        never inside an eval loop.  With grid_storage == "bf16" the struct points at the bfloat16
+        copies of the grids (additionally keyed on the grids' version counters) unless `fp32` is set
+        (the autograd node: forward and backward read the live fp32 parameters)."""
         # (read through the modules' _parameters / _modules dicts: ParameterList / Sequential indexing
         #  costs ~1 us per access, and this runs on every render call)
         mods = self._modules
@@ -512,16 +567,19 @@ class TensorBase(torch.nn.Module):
         grids = (*mods["density_plane"]._parameters.values(), *mods["density_line"]._parameters.values(),
                  *mods["app_plane"]._parameters.values(), *mods["app_line"]._parameters.values())
         am = self.alphaMask
+        use16 = self.grid_storage == "bf16" and not fp32
         k_struct = (tuple(t.data_ptr() for t in grids + mlp), z.data_ptr(), z.numel(),
                     None if am is None else (am.alpha_volume.data_ptr(), am.aabb._version),
                     self.aabb._version, tuple(self._grid_host), float(self.density_shift),
-                    float(self.distance_scale), float(self.rayMarch_weight_thres), self.fea2denseAct)
-        memo = self.__dict__.get("_fs_memo")
+                    float(self.distance_scale), float(self.rayMarch_weight_thres), self.fea2denseAct,
+                    tuple(t._version for t in grids) if use16 else None)
+        slot = "_fs16_memo" if use16 else "_fs_memo"
+        memo = self.__dict__.get(slot)
         if memo is None or memo[0] != k_struct:
-            fs, keep = self._field_struct(z)
+            fs, keep = self._field_struct(z, grid16=use16)
             # hold every tensor whose address the struct stores: no recycled pointers while cached
             memo = (k_struct, fs, keep, grids + mlp + (z,) + (() if am is None else (am.alpha_volume,)))
-            self.__dict__["_fs_memo"] = memo
+            self.__dict__[slot] = memo
         fs = memo[1]
         k_prep = tuple((t.data_ptr(), t._version) for t in mlp)
         pm = self.__dict__.get("_prep_memo")
@@ -620,11 +678,11 @@ class TensorBase(torch.nn.Module):
             self.__dict__["_bprep_memo"] = memo
         return memo[1]
 
-    def _render_fused(self, rays, z, bg, floater_thresh, return_weights, stats, refine=True):
+    def _render_fused(self, rays, z, bg, floater_thresh, return_weights, stats, refine=True, fp32=False):
         """One lrf_render launch on explicit rays [n,6] (contiguous fp32) -> (rgb [n,3], depth [n])."""
         dev, n = rays.device, rays.shape[0]
         with torch.cuda.device(dev):
-            fs, prep = self.field_and_prepared(z)
+            fs, prep = self.field_and_prepared(z, fp32=fp32)
             rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
             depth = torch.empty(n, dtype=torch.float32, device=dev)
             weights = torch.empty(n, z.numel(), dtype=torch.float32, device=dev) if return_weights else None

@@ -75,3 +75,23 @@ def test_backward_sizes_and_validation_without_gpu():
     assert rc == -1 and b"prepared_bwd" in L.lrf_last_error()
     rc = L.lrf_field_prepare_backward(C.byref(f), None, None)
     assert rc == -1
+
+
+def test_grid_dtype_validation_without_gpu():
+    """bf16 grid storage (LrfField.grid_dtype) is accepted by the inference entries only; anything else
+    refuses it before touching a device instead of reading 16-bit texels as fp32."""
+    L = _lib.lib()
+    # grid_dtype sits in what used to be tail padding: the offset is part of the ABI
+    assert _lib.LrfField.grid_dtype.offset == _lib.LrfField.n_samples.offset + 4
+    f = _lib.LrfField()
+    f.n_dcomp, f.n_acomp = 8, 24
+    f.grid_dtype = 7
+    assert L.lrf_density_feature(C.byref(f), None, 0, None, None) == -1 and b"grid_dtype" in L.lrf_last_error()
+    f.grid_dtype = _lib.GRID_BF16
+    for call in (lambda: L.lrf_app_products(C.byref(f), None, 0, None, None),
+                 lambda: L.lrf_density_l1(C.byref(f), None, None),
+                 lambda: L.lrf_density_feature_backward(C.byref(f), None, None, 0, (C.c_void_p * 3)(), (C.c_void_p * 3)(), None, None)):
+        assert call() == -2 and b"bf16 grid storage" in L.lrf_last_error()
+    assert L.lrf_density_feature(C.byref(f), None, 0, None, None) == -1      # accepted: fails later, on gridSize 0
+    assert b"gridSize" in L.lrf_last_error()
+    assert L.lrf_pack_bf16(None, None, -1, None) == -1

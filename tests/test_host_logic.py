@@ -100,3 +100,26 @@ def test_test_frame_exposure_rule():
         vm = max(v - 1, 0); vm = 1 if vm == v else vm
         vp = min(v + 1, n - 1); vp = n - 2 if vm == v else vp
         torch.testing.assert_close(out, (E[vm] + E[vp]) / 2)
+
+
+def test_grid_storage_setting_host_side():
+    """set_grid_storage: validation, propagation through LocalTensorfs, inheritance by appended fields; the
+    parameters and the state_dict are untouched (the 16-bit copies are an inference cache)."""
+    from gpu_helpers import module_from_golden, local_from_golden
+    m = module_from_golden(load_golden("opaque_32"), device="cpu")
+    keys = set(m.state_dict().keys())
+    assert m.grid_storage == "fp32"
+    with pytest.raises(ValueError):
+        m.set_grid_storage("fp16")
+    assert m.set_grid_storage("bf16") is m and m.grid_storage == "bf16"
+    assert set(m.state_dict().keys()) == keys and all(p.dtype == torch.float32 for p in m.parameters())
+    m.set_grid_storage("fp32")
+    pe = module_from_golden(load_golden("aniso_pe"), device="cpu")
+    with pytest.raises(NotImplementedError):
+        pe.set_grid_storage("bf16")
+    lt = local_from_golden(load_golden("local3"), device="cpu")
+    lt.set_grid_storage("bf16")
+    assert all(rf.grid_storage == "bf16" for rf in lt.tensorfs)
+    n = len(lt.tensorfs)
+    lt.append_frame(); lt.append_rf(1)
+    assert len(lt.tensorfs) == n + 1 and lt.tensorfs[-1].grid_storage == "bf16"
