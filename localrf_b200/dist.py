@@ -65,6 +65,39 @@ def gather_pixels(rgb, depth, n_total, group=None):
     return full[:, :3].contiguous(), full[:, 3].contiguous()
 
 
+class ExchangeSchedule:
+    """The step bookkeeping of the fused pixel exchange, free of any device state (PixelExchange owns one;
+    tests/test_dist_gloo.py drives N of them through randomly interleaved simulated ranks to check the
+    protocol's two claims: a gathered image is complete when it is read, and no buffer is overwritten before
+    every rank has read it -- for any N, any lag, any relative speed of the ranks).
+
+    Steps are numbered from 1.  `seq` = steps this rank has launched."""
+
+    def __init__(self, lag=0):
+        self.lag = int(lag)
+        if self.lag < 0:
+            raise ValueError("lag must be >= 0")
+        self.n_buf = 2 if self.lag == 0 else 2 * self.lag + 4
+        self.seq = 0
+
+    def next_step(self):
+        """-> (buffer index the NEXT step's pixels go to, the step number its last CTA publishes, the step of
+        the peers its prologue waits for (0 = no wait: lag 0 closes the step with a separate wait kernel))"""
+        step = self.seq + 1
+        wait = max(self.seq - self.lag, 0) if self.lag >= 1 else 0
+        return step % self.n_buf, step, wait
+
+    def advance(self):
+        self.seq += 1
+
+    def gathered_step(self):
+        """The step whose complete image is readable now (after the launch of step `seq`, in stream order)."""
+        return self.seq if self.lag == 0 else max(self.seq - 1 - self.lag, 0)
+
+    def gathered_buffer(self):
+        return self.gathered_step() % self.n_buf
+
+
 class PixelExchange:
     """Gathered pixel buffer in symmetric memory + the step barrier (fused pixel exchange).
 
@@ -92,8 +125,8 @@ class PixelExchange:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.max_rays = int(max_rays)
         self.buf_bytes = (self.max_rays * 16 + 255) // 256 * 256
-        self.lag = int(lag)
-        self.n_buf = 2 if self.lag == 0 else 2 * self.lag + 4
+        self.sched = ExchangeSchedule(lag)
+        self.lag, self.n_buf = self.sched.lag, self.sched.n_buf
         total = self.n_buf * self.buf_bytes + self.FLAG_BYTES
         self.mem = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
         self.mem.zero_()
@@ -108,7 +141,6 @@ class PixelExchange:
             except Exception:
                 mc = 0
         self.mc_ptr = mc
-        self.seq = 0
         self._flag_ptrs = (C.c_void_p * self.world)(*[p + self.n_buf * self.buf_bytes for p in self.ptrs])
         self._lib = _lib
         dist.barrier(self.group)          # every rank has zeroed + mapped before anybody stores
@@ -116,7 +148,8 @@ class PixelExchange:
     def fill_outputs(self, o, ray_lo):
         """Points an LrfOutputs at the NEXT step's buffer: peer p receives this rank's rays at row
         `ray_lo` of its gathered buffer."""
-        off = ((self.seq + 1) % self.n_buf) * self.buf_bytes + ray_lo * 16
+        buf, signal_seq, wait_seq = self.sched.next_step()
+        off = buf * self.buf_bytes + ray_lo * 16
         o.n_peers = self.world
         for p in range(self.world):
             o.peer_pix[p] = self.ptrs[p] + off
@@ -125,30 +158,34 @@ class PixelExchange:
         # the kernel itself publishes the step (its last CTA release-stores the flags after all pixel
         # stores) and, when the consumer lags, first waits for the peers to be done with this buffer
         o.rank = self.rank
-        o.signal_seq = self.seq + 1
-        o.wait_seq = max(self.seq - self.lag, 0) if self.lag >= 1 else 0
+        o.signal_seq = signal_seq
+        o.wait_seq = wait_seq
 
     def close_step(self, stream):
         """Closes the step the render kernel has just published.  lag 0: enqueues the wait for every peer's
         flag of THIS step (one small kernel); lag >= 1: nothing to enqueue.  `gathered(n)` then refers to
         step (this - 0) resp. (this - 1 - lag), which is complete at that point of the stream."""
-        self.seq += 1
+        self.sched.advance()
         if self.lag == 0:
             self._lib.check(self._lib.lib().lrf_peer_signal_wait(self._flag_ptrs, self.rank, self.world, self.seq,
                                                                  self.seq, stream))
 
     def skip_step(self, stream):
         """A rank whose shard of this step is empty renders nothing but still publishes the step."""
-        self.seq += 1
+        self.sched.advance()
         self._lib.check(self._lib.lib().lrf_peer_signal_wait(self._flag_ptrs, self.rank, self.world, self.seq,
                                                              self.seq if self.lag == 0 else 0, stream))
 
+    @property
+    def seq(self):
+        return self.sched.seq
+
     def gathered_step(self):
         """The step whose complete image `gathered()` returns now."""
-        return self.seq if self.lag == 0 else max(self.seq - 1 - self.lag, 0)
+        return self.sched.gathered_step()
 
     def gathered(self, n_rays):
-        off = (self.gathered_step() % self.n_buf) * self.buf_bytes
+        off = self.sched.gathered_buffer() * self.buf_bytes
         return self.mem[off:off + n_rays * 16].view(torch.float32).view(n_rays, 4)
 
 
