@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload cfg2|distB|incoherent|cfg3|cfg5] [--scaling weak|strong|frame]
-                    [--exchange fused|nccl]
+                    [--exchange fused|nccl] [--lag L] [--grid-storage fp32|bf16]
 
 Workloads (fields built by the reference's constructor defaults, random init):
   cfg2        (default, the headline) one TensorVMSplit at 300^3, seed 0, an 800x800 pinhole frame at
@@ -40,8 +40,11 @@ N > 1 (torchrun, one rank per GPU), field replicated, rays sharded, no data-path
   finishes a ray stores it into every peer's gathered buffer (symmetric memory over NVLink/NVSwitch,
   NVLS multicast when available); the kernel's last CTA publishes the step in every peer's flag array and
   the next launches wait (in their prologue) for the peers' step s-1-lag -- no barrier launch, no collective
-  (--exchange fused, --lag 1 default; --lag 0 = same-step barrier kernel); --exchange nccl uses one
+  (--exchange fused, --lag 3 default; --lag 0 = same-step barrier kernel); --exchange nccl uses one
   ncclAllGather per step instead.
+
+--grid-storage bf16 (NOT the headline; a separate, labelled line): eval kernels gather bfloat16 copies of the
+  grids (LocalTensorfs.set_grid_storage); the roofline then counts 288 / 864 B per density / appearance sample.
 """
 import argparse
 import json
