@@ -586,7 +586,8 @@ def main():
     st = stats.cpu().tolist()
     value = rays_per_step_global * args.steps / (total_ms * 1e-3)
     launches = [len(p.launches) for p in lt.__dict__.get("_plans", {}).values()]
-    gpu_launches = args.steps * (max(launches) if launches else 1) + (args.steps if xch is not None else 0)
+    # (+ one barrier kernel per step only for the same-step exchange; with slack the render kernel signals itself)
+    gpu_launches = args.steps * (max(launches) if launches else 1) + (args.steps if xch is not None and xch.lag == 0 else 0)
 
     # N > 1: what a step costs on each rank without any exchange (per-rank events, max over ranks): separates
     # the kernel from the exchange / rank-desynchronisation share of ms_per_step
