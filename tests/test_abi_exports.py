@@ -95,3 +95,45 @@ def test_grid_dtype_validation_without_gpu():
     assert L.lrf_density_feature(C.byref(f), None, 0, None, None) == -1      # accepted: fails later, on gridSize 0
     assert b"gridSize" in L.lrf_last_error()
     assert L.lrf_pack_bf16(None, None, -1, None) == -1
+
+
+def test_header_is_plain_c_and_struct_layout_matches(tmp_path):
+    """include/localrf_b200.h compiles as C99 (gcc -pedantic -Werror: no C++-isms, no torch / CUDA types in the
+    boundary) and a C program that dlopens the library sees the same struct sizes and field offsets as the
+    ctypes mirrors -- i.e. a cgo / JNI / plain-C host can bind it as INTEGRATION.md describes."""
+    import subprocess
+    src = tmp_path / "abi_check.c"
+    src.write_text(r'''
+#include <dlfcn.h>
+#include <stddef.h>
+#include <stdio.h>
+#include "localrf_b200.h"
+int main(int argc, char **argv) {
+  void *h = argc > 1 ? dlopen(argv[1], RTLD_NOW | RTLD_LOCAL) : NULL;
+  if (!h) { fprintf(stderr, "%s\n", dlerror()); return 2; }
+  size_t (*sz)(int32_t) = NULL;
+  int (*ver)(void) = NULL;
+  *(void **)(&sz) = dlsym(h, "lrf_sizeof");        /* the POSIX idiom for dlsym -> function pointer */
+  *(void **)(&ver) = dlsym(h, "lrf_version");
+  if (!sz || !ver) return 3;
+  if (sz(0) != sizeof(LrfField) || sz(1) != sizeof(LrfBatch) || sz(2) != sizeof(LrfOutputs) ||
+      sz(3) != sizeof(LrfGradients)) return 4;
+  printf("%d %zu %zu %zu %zu %zu %zu %zu\n", ver(), sizeof(LrfField), offsetof(LrfField, grid_dtype),
+         offsetof(LrfField, z_vals), offsetof(LrfBatch, refine), offsetof(LrfOutputs, peer_flags),
+         offsetof(LrfOutputs, wait_seq), offsetof(LrfGradients, d_b3));
+  return 0;
+}
+''')
+    exe = tmp_path / "abi_check"
+    env = dict(os.environ); env.pop("CC", None)
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-o", str(exe), str(src), "-ldl"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    _lib.lib()                                                     # (builds the library if needed)
+    r = subprocess.run([str(exe), _lib.LIB_PATH], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    got = [int(v) for v in r.stdout.split()]
+    want = [_lib.ABI_VERSION, C.sizeof(_lib.LrfField), _lib.LrfField.grid_dtype.offset, _lib.LrfField.z_vals.offset,
+            _lib.LrfBatch.refine.offset, _lib.LrfOutputs.peer_flags.offset, _lib.LrfOutputs.wait_seq.offset,
+            _lib.LrfGradients.d_b3.offset]
+    assert got == want
