@@ -136,10 +136,9 @@ class _RenderFn(torch.autograd.Function):
             fs, _ = m.field_and_prepared(z, fp32=True)
             bp = m._prepared_backward()
             need = lib.lrf_backward_scratch_bytes(n, z.numel())
-            scratch = m.__dict__.get("_bwd_scratch")
-            if scratch is None or scratch.device != dev or scratch.numel() < need:
-                scratch = torch.empty(need, dtype=torch.uint8, device=dev)
-                m.__dict__["_bwd_scratch"] = scratch
+            # per call, from torch's caching allocator (stream-ordered reuse): backwards of the same module on
+            # different streams never share a scratch block
+            scratch = torch.empty(need, dtype=torch.uint8, device=dev)
             g = _lib.LrfGradients()
             g.d_rays = d_rays.data_ptr()
             for i in range(3):
