@@ -105,4 +105,10 @@ void emul_split8(const float* v, float* hi, float* lo) {
   }
 }
 
+// byte offset of element (row, k) in a K-major, no-swizzle core-matrix operand image (lrf_common.cuh)
+int emul_oper_offset(int row, int k, int chunks) { return oper_offset(row, k, chunks); }
+// sizes of the prepared blocks as the headers compute them
+int emul_prep_bytes(void) { return PREP_BYTES; }
+int emul_pe_prepared_bytes(int fea_pe) { return pe_prepared_bytes(fea_pe); }
+
 }  // extern "C"

@@ -196,3 +196,26 @@ def test_hi_lo_split_keeps_16_mantissa_bits(emul):
     assert np.abs((hi.astype(np.float64) + lo) - v).max() <= 2.0 ** -16 * np.abs(v).max()
     assert (np.abs(hi.astype(np.float64) + lo - v) <= 2.0 ** -16 * np.abs(v)).all()
     assert np.array_equal(hi, torch.from_numpy(v).to(torch.bfloat16).to(torch.float32).numpy())
+
+
+def test_operand_image_layout_and_prepared_sizes(emul):
+    """oper_offset is the canonical K-major / no-swizzle tcgen05 operand image: 8 x 8 core matrices of 128 contiguous
+    bytes, LBO = 128 B between K-adjacent core matrices, SBO = chunks * 128 B between 8-row groups (the strides
+    issue_layer puts into the shared-memory descriptors) -- a bijection onto the image; and the prepared-block sizes
+    the C ABI reports are the ones the headers lay out."""
+    from localrf_b200 import _lib
+    for rows, K in ((128, 80), (128, 128), (32, 80), (128, 64)):
+        chunks = K // 8
+        seen = set()
+        for r in range(rows):
+            for k in range(K):
+                off = emul.emul_oper_offset(r, k, chunks)
+                assert off == (r >> 3) * chunks * 128 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2
+                seen.add(off)
+        assert seen == set(range(0, rows * K * 2, 2))
+    L = _lib.lib()
+    assert emul.emul_prep_bytes() == L.lrf_prepared_bytes()
+    f = _lib.LrfField()
+    for pe in (1, 3, 6, 8):
+        f.fea_pe, f.view_pe = pe, 0
+        assert emul.emul_pe_prepared_bytes(pe) == L.lrf_prepared_bytes_for(C.byref(f))
