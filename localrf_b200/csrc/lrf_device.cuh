@@ -7,6 +7,16 @@
 
 namespace lrf {
 
+// Experiment switch (DESIGN.md par. 10, code size): LRF_ROLL_PLANES=1 keeps the loop over the three planes of the
+// VM gathers ROLLED (a third of the gather code, plane geometry indexed at run time); 0 = fully unrolled (default).
+#ifndef LRF_ROLL_PLANES
+#define LRF_ROLL_PLANES 0
+#endif
+#if LRF_ROLL_PLANES
+#define LRF_PLANE_LOOP _Pragma("unroll 1")
+#else
+#define LRF_PLANE_LOOP _Pragma("unroll")
+#endif
 
 constexpr int TM = 128;      // appearance samples per MLP sub-tile (= UMMA M)
 constexpr int TMEM_COLS = 512;   // power of two >= 384 used columns
@@ -307,7 +317,7 @@ __device__ __forceinline__ float alpha_mask(const FieldDev& F, const float* p) {
 // compute_densityfeature for one point (tensoRF.py:112-151), channel-last planes/lines
 __device__ __forceinline__ float density_feature(const FieldDev& F, const float* q) {
   float sigma = 0.0f;
-#pragma unroll
+LRF_PLANE_LOOP
   for (int i = 0; i < 3; ++i) {
     const int W = F.g[mat0(i)], H = F.g[mat1(i)], L = F.g[vecm(i)];
     int x0, x1, y0, y1, l0, l1;
@@ -395,7 +405,7 @@ __device__ __forceinline__ Tex8 ldg8_bf16(const __nv_bfloat16* p) {
 __device__ __forceinline__ float density_feature_bf16(const FieldDev& F, const float* q) {
   static_assert(CD == 8, "one 16-byte load per density texel");
   float sigma = 0.0f;
-#pragma unroll
+LRF_PLANE_LOOP
   for (int i = 0; i < 3; ++i) {
     const int W = F.g[mat0(i)], H = F.g[mat1(i)], L = F.g[vecm(i)];
     int x0, x1, y0, y1, l0, l1;

@@ -193,7 +193,7 @@ __device__ __forceinline__ void finalize_slot(const BatchDev& B, Slot* s) {
 // 72 appearance products of one sample -> one row of the A1 tile (bf16 hi/lo, 9 chunks of 8)
 __device__ __forceinline__ void app_row(const FieldDev& F, const float* q, unsigned char* a_hi,
                                         unsigned char* a_lo, int row) {
-#pragma unroll
+LRF_PLANE_LOOP
   for (int i = 0; i < 3; ++i) {
     const int W = F.g[mat0(i)], H = F.g[mat1(i)], L = F.g[vecm(i)];
     int x0, x1, y0, y1, l0, l1;
@@ -232,7 +232,7 @@ __device__ __forceinline__ void app_row(const FieldDev& F, const float* q, unsig
 // the same row from bf16 texels (LrfField.grid_dtype = LRF_GRID_BF16): three 16-byte loads per texel
 __device__ __forceinline__ void app_row_bf16(const FieldDev& F, const float* q, unsigned char* a_hi,
                                              unsigned char* a_lo, int row) {
-#pragma unroll
+LRF_PLANE_LOOP
   for (int i = 0; i < 3; ++i) {
     const int W = F.g[mat0(i)], H = F.g[mat1(i)], L = F.g[vecm(i)];
     int x0, x1, y0, y1, l0, l1;
