@@ -1,6 +1,10 @@
 """Experiment (DESIGN.md par. 10, code size): time cfg2 batches with an alternative build of the library
 (e.g. -DLRF_ROLL_PLANES=1) and dump one batch's pixels for comparison with the default build.
-    python tools/roll_planes.py <path to .so> <tag>"""
+    python tools/roll_planes.py <path to .so> <tag>
+The variant of tools/gpu_call19.sh was built with
+    cd localrf_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC \
+        -shared -DLRF_ROLL_PLANES=1 -o liblrf_b200_roll.so lrf_render.cu lrf_aux.cu lrf_grad.cu lrf_backward.cu \
+        lrf_sched.cu lrf_abi.cu"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
